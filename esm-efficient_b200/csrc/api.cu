@@ -1,0 +1,81 @@
+// extern "C" surface of libesmk.so (see include/esmk.h).  Thin forwarding layer:
+// validates nothing itself, converts the opaque stream handle, never throws.
+#include <atomic>
+
+#include "common.cuh"
+#include "esmk_internal.h"
+
+struct esmk_model;
+
+namespace esmk {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace esmk
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define GUARD(expr)                                   \
+  try {                                               \
+    return (expr);                                    \
+  } catch (const std::exception& e) {                 \
+    return ::esmk::fail("esmk", e.what());            \
+  } catch (...) {                                     \
+    return ::esmk::fail("esmk", "unknown exception"); \
+  }
+
+extern "C" {
+
+const char* esmk_last_error(void) { return esmk::last_error().c_str(); }
+int esmk_version(void) { return 100; }
+uint64_t esmk_launch_count(void) { return esmk::launch_count(); }
+
+int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, esmk_stream_t s) {
+  GUARD(esmk::batch_meta(cu_lens, B, T, pos, tile_cu, ST(s)));
+}
+int esmk_rope_tables(void* cosb, void* sinb, int max_len, int head_dim, esmk_stream_t s) {
+  GUARD(esmk::rope_tables(cosb, sinb, max_len, head_dim, ST(s)));
+}
+int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
+               const uint8_t* zero_rows, esmk_stream_t s) {
+  GUARD(esmk::embed(tokens, table, out, T, D, vocab, zero_token, zero_rows, ST(s)));
+}
+int esmk_layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
+                   esmk_stream_t s) {
+  GUARD(esmk::layernorm(x, ldx, w, b, y, ldy, T, D, eps, ST(s)));
+}
+int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_dim, const void* lnq, const void* lnk,
+                      const void* cosb, const void* sinb, const int32_t* pos, esmk_stream_t s) {
+  GUARD(esmk::qk_norm_rope(q, k, ld, T, H, head_dim, lnq, lnk, cosb, sinb, pos, ST(s)));
+}
+int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t s) {
+  GUARD(esmk::softmax(logits, ld_in, out, ld_out, T, V, log, ST(s)));
+}
+int esmk_gemm(const esmk_gemm_args* a, esmk_stream_t s) {
+  if (a == nullptr) return esmk::fail("esmk_gemm", "null args");
+  GUARD(esmk::gemm(*a, ST(s)));
+}
+int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
+                     const int32_t* tile_cu, int B, int T, int H, int head_dim, int max_len, int impl,
+                     esmk_stream_t s) {
+  GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_cu, B, T, H, head_dim, max_len, impl, ST(s)));
+}
+int esmk_model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model_t** out) {
+  GUARD(esmk::model_create(cfg, w, out));
+}
+void esmk_model_destroy(esmk_model_t* m) { delete m; }
+size_t esmk_workspace_bytes(const esmk_model_t* m, int T, int B, int max_len) {
+  if (m == nullptr || T < 1 || B < 1 || max_len < 1) return 0;
+  return esmk::workspace_bytes(m, T, B, max_len);
+}
+int esmk_forward(esmk_model_t* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,
+                 const uint8_t* zero_rows, void* workspace, size_t workspace_bytes, int output_kind, void* out,
+                 void* const* layer_taps, esmk_stream_t s) {
+  GUARD(esmk::forward(m, tokens, cu_lens, T, B, max_len, zero_rows, workspace, workspace_bytes, output_kind, out,
+                      layer_taps, ST(s)));
+}
+int esmk_lm_head(esmk_model_t* m, const void* x, int T, void* workspace, size_t workspace_bytes, int output_kind,
+                 void* out, esmk_stream_t s) {
+  GUARD(esmk::lm_head(m, x, T, workspace, workspace_bytes, output_kind, out, ST(s)));
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// Variable-length (cu_seqlens-packed) multi-head attention, non-causal.
+//
+// attn64_kernel (head_dim 64): one CTA per (128-query tile, head).
+//   warp 0     : TMA producer  (Q once; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B)
+//   warp 1     : tcgen05.mma issuer:  S = Q K_j^T  (UMMA 128x128x16, K-major operands)
+//                                      O_j = P_j V_j (UMMA 128x64x16, P K-major from smem, V MN-major)
+//   warps 2..5 : online softmax, one query row per thread: S is read from TMEM
+//                (tcgen05.ld), P is rounded to bf16 and written to shared memory in
+//                the 128-byte-swizzled UMMA layout, O_j is read back from TMEM and
+//                accumulated in registers with the running-max correction.
+//   Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's
+//   softmax overlaps the other's MMAs.
+//
+// attn_generic_kernel: CUDA-core kernel for other head dims (e.g. ESM2-8M, hd=16)
+//   and the on-device cross-check of the tcgen05 kernel.
+//
+// Semantics follow flash_attn_varlen_func as called at esme/attention.py:115-123:
+// scale hd^-0.5, fp32 scores, un-normalised P rounded to bf16 before P.V, fp32 row
+// sums of the un-rounded P, one final rounding of O.
+#include "common.cuh"
+#include "esmk_internal.h"
+
+namespace esmk {
+
+namespace {
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 kernel, head_dim = 64
+// ---------------------------------------------------------------------------
+constexpr int AT_THREADS = 192;
+constexpr int TILE = 128;            // query rows per CTA == keys per block
+constexpr int HD64 = 64;
+constexpr int Q_BYTES = TILE * HD64 * 2;   // 16 KB
+constexpr int P_BYTES = TILE * TILE * 2;   // 32 KB (two 128x64 swizzle atoms)
+constexpr int AT_SMEM = Q_BYTES * 3 + P_BYTES + 1024 + 128;
+constexpr int AT_TMEM_COLS = 256;    // S: [0,128)  O: [128,192)
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
+              const int32_t* __restrict__ cu_lens, const int32_t* __restrict__ tile_cu, int B, float scale_log2) {
+  // ---- which (sequence, query tile) is this CTA? ----
+  const int tq = blockIdx.x;
+  if (tq >= tile_cu[B]) return;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (tile_cu[mid] <= tq) lo = mid; else hi = mid;
+  }
+  const int seq_start = cu_lens[lo];
+  const int L = cu_lens[lo + 1] - seq_start;
+  const int q0 = (tq - tile_cu[lo]) * TILE;
+  const int n_kv = (L + TILE - 1) / TILE;
+  const int head = blockIdx.y;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + Q_BYTES;
+  uint8_t* sP = sV + Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_empty = bars + 4;
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_q, 1);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int col = head * HD64;
+      mbar_arrive_expect_tx(bar_q, Q_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, col, seq_start + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = j & 1;
+        const int krow = seq_start + j * TILE;
+        mbar_wait(k_empty, ph ^ 1);
+        mbar_arrive_expect_tx(k_full, Q_BYTES);
+        tma_load_2d(sK, &tmK, k_full, col, krow);
+        mbar_wait(v_empty, ph ^ 1);
+        mbar_arrive_expect_tx(v_full, Q_BYTES);
+        tma_load_2d(sV, &tmV, v_full, col, krow);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : V is MN-major
+      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, 1024, 2);
+      const uint64_t kdesc = make_smem_desc(smem_u32(sK), 16, 1024, 2);
+      const uint64_t vdesc = make_smem_desc(smem_u32(sV), 1024, 1024, 2);
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(sP), 16, 1024, 2);
+      const uint64_t pdesc1 = make_smem_desc(smem_u32(sP + TILE * 128), 16, 1024, 2);
+
+      mbar_wait(bar_q, 0);
+      mbar_wait(k_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      umma_commit(s_full);
+      umma_commit(k_empty);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(p_full, ph);
+        mbar_wait(v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TILE / 16; ++k) {
+          // P: 16 keys = 32 bytes inside a 64-key swizzle atom; V: 16 key rows = 2048 bytes
+          const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+          umma_ss(tmem_O, pd, vdesc + (k * 2048 >> 4), idesc_o, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(v_empty);
+        if (j + 1 < n_kv) {
+          mbar_wait(k_full, ph ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+          umma_commit(k_empty);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / accumulate =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[HD64];
+#pragma unroll
+    for (int i = 0; i < HD64; ++i) acc[i] = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int rsw = r & 7;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t ph = j & 1;
+      const int kv_valid = L - j * TILE;  // keys [0, kv_valid) of this block exist
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // ---- pass 1: row maximum ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, s);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float alpha = fast_exp2(m_run - m_new);  // m_run = -inf on the first block -> 0
+      // ---- pass 2: P = exp2(S*c - m), bf16, to shared memory in UMMA K-major SW128 layout ----
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, s);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < kv_valid) ? fast_exp2(__uint_as_float(s[i]) * scale_log2 - m_new) : 0.f;
+          float p1 = (c * 32 + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(s[i + 1]) * scale_log2 - m_new) : 0.f;
+          rowsum += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // keys [c*32, c*32+32) -> atom (c>>1), 16-byte chunks ((c&1)*4 .. +3) of this row, XOR-swizzled by row&7
+        uint8_t* atom = prow + (c >> 1) * (TILE * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ rsw;
+          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * alpha + rowsum;
+      m_run = m_new;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();         // our tcgen05.ld of S are complete before the MMA warp overwrites S
+      mbar_arrive(p_full);
+#pragma unroll
+      for (int i = 0; i < HD64; ++i) acc[i] *= alpha;
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tmem_O + lane_off, o0);
+        tmem_ld32(tmem_O + lane_off + 32, o1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { acc[i] += __uint_as_float(o0[i]); acc[32 + i] += __uint_as_float(o1[i]); }
+      }
+    }
+    if (q0 + r < L) {
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + head * HD64;
+#pragma unroll
+      for (int i = 0; i < HD64; i += 8)
+        *reinterpret_cast<uint4*>(dst + i) =
+            make_uint4(pack_bf16(acc[i] * inv, acc[i + 1] * inv), pack_bf16(acc[i + 2] * inv, acc[i + 3] * inv),
+                       pack_bf16(acc[i + 4] * inv, acc[i + 5] * inv), pack_bf16(acc[i + 6] * inv, acc[i + 7] * inv));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CUDA-core kernel: one warp per (query token, head); lanes = keys for the
+// scores, lanes = output features for P.V.
+// ---------------------------------------------------------------------------
+constexpr int GEN_WARPS = 4;
+
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+attn_generic_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                    const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ out, int ldo,
+                    const int32_t* __restrict__ cu_lens, int B, int T, int hd, float scale_log2) {
+  __shared__ float sq[GEN_WARPS][128];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * GEN_WARPS + w;
+  const int head = blockIdx.y;
+  if (t >= T) return;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cu_lens[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int s0 = cu_lens[lo], L = cu_lens[lo + 1] - s0;
+  const __nv_bfloat16* qrow = q + (size_t)t * ld + head * hd;
+  for (int d = lane; d < hd; d += 32) sq[w][d] = __bfloat162float(qrow[d]);
+  __syncwarp();
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    const int j = j0 + lane;
+    float s = -INFINITY;
+    if (j < L) {
+      const uint4* kr = reinterpret_cast<const uint4*>(k + (size_t)(s0 + j) * ld + head * hd);
+      float dot = 0.f;
+      for (int c = 0; c < hd / 8; ++c) {
+        const uint4 u = __ldg(kr + c);
+        const float* qq = &sq[w][c * 8];
+        dot += qq[0] * bf16_lo(u.x) + qq[1] * bf16_hi(u.x) + qq[2] * bf16_lo(u.y) + qq[3] * bf16_hi(u.y) +
+               qq[4] * bf16_lo(u.z) + qq[5] * bf16_hi(u.z) + qq[6] * bf16_lo(u.w) + qq[7] * bf16_hi(u.w);
+      }
+      s = dot * scale_log2;
+    }
+    float mx = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f(m_run - m_new);
+    const float p = (j < L) ? exp2f(s - m_new) : 0.f;
+    float ps = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    l_run = l_run * alpha + ps;
+    m_run = m_new;
+    const float pb = bfr(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] *= alpha;
+    const int nk = min(32, L - j0);
+    for (int jj = 0; jj < nk; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, pb, jj);
+      const __nv_bfloat16* vr = v + (size_t)(s0 + j0 + jj) * ld + head * hd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        if (d < hd) acc[i] += pj * __bfloat162float(vr[d]);
+      }
+    }
+  }
+  __nv_bfloat16* orow = out + (size_t)t * ldo + head * hd;
+  const float inv = 1.0f / l_run;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < hd) orow[d] = __float2bfloat16_rn(acc[i] * inv);
+  }
+}
+
+}  // namespace
+
+int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
+                const int32_t* tile_cu, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st) {
+  ESMK_REQUIRE(B >= 1 && T >= 1 && H >= 1, "empty attention problem");
+  ESMK_REQUIRE(hd % 8 == 0 && hd <= 128, "head_dim must be a multiple of 8 and <= 128");
+  ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
+  const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
+  if (hd == 64 && impl == 0) {
+    ESMK_REQUIRE(tile_cu != nullptr, "tile_cu (esmk_batch_meta) required");
+    CUtensorMap tq, tk, tv;
+    ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
+    ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
+    ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
+    static bool configured = false;
+    if (!configured) {
+      ESMK_CUDA(cudaFuncSetAttribute(attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      configured = true;
+    }
+    dim3 grid((T + TILE - 1) / TILE + B, H);
+    attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
+                                                      scale_log2);
+  } else {
+    dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
+    attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                          (const __nv_bfloat16*)v, ld, (__nv_bfloat16*)out, ldo,
+                                                          cu_lens, B, T, hd, scale_log2);
+  }
+  (void)max_len;
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace esmk

@@ -1,0 +1,39 @@
+// Internal C++ interface between the kernel translation units and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/esmk.h"
+
+namespace esmk {
+
+const std::string& last_error();
+void count_launch(int n = 1);
+uint64_t launch_count();
+
+int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, cudaStream_t st);
+int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st);
+int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
+          const uint8_t* zero_rows, cudaStream_t st);
+int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
+              cudaStream_t st);
+int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,
+                 const void* sinb, const int32_t* pos, cudaStream_t st);
+int softmax(const void* x, int ldx, void* y, int ldy, int T, int V, int log_mode, cudaStream_t st);
+
+int gemm(const esmk_gemm_args& a, cudaStream_t st);
+
+int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
+                const int32_t* tile_cu, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st);
+
+int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out);
+size_t workspace_bytes(const esmk_model* m, int T, int B, int max_len);
+int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,
+            const uint8_t* zero_rows, void* workspace, size_t workspace_bytes, int kind, void* out,
+            void* const* layer_taps, cudaStream_t st);
+int lm_head(esmk_model* m, const void* x, int T, void* workspace, size_t workspace_bytes, int kind, void* out,
+            cudaStream_t st);
+
+}  // namespace esmk

@@ -1,0 +1,367 @@
+// C[M,N] = epilogue(A[M,K] . W[N,K]^T): persistent, warp-specialised tcgen05 GEMM.
+//
+//   warp 0      : TMA producer (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, 4-stage ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, fp32 accum in TMEM)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+//
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Tiles are walked n-fastest so the CTAs
+// resident at any time share a handful of A row-blocks and the whole of W in L2.
+//
+// Fused epilogues reproduce the reference's bf16 rounding points (SURVEY.md
+// Appendix A): see enum esmk_epilogue in include/esmk.h.
+#include "common.cuh"
+#include "esmk_internal.h"
+
+namespace esmk {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_STAGE = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE = BN * BK * 2;  // 32 KB
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct EpiParams {
+  __nv_bfloat16* C;
+  int ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* R;
+  int ldr;
+  float scale;  // residue_scaling (divisor)
+  const __nv_bfloat16* cosb;
+  const __nv_bfloat16* sinb;
+  const int32_t* pos;
+  int rope_cols;
+  int vec_ok;  // 16-byte stores allowed (N, ldc, ldr multiples of 8)
+};
+
+// ---- epilogue math on one 64-column group held in registers -----------------
+template <int HD>
+__device__ __forceinline__ void rope64(float (&v)[64], const uint32_t (&cs)[HD / 2]) {
+  // cs[i] packs (cos[i], sin[i]) as bf16 pairs for i in [0, HD/2)
+#pragma unroll
+  for (int h = 0; h < 64 / HD; ++h) {
+#pragma unroll
+    for (int i = 0; i < HD / 2; ++i) {
+      const float c = bf16_lo(cs[i]), s = bf16_hi(cs[i]);
+      const float a = v[h * HD + i], b = v[h * HD + i + HD / 2];
+      v[h * HD + i] = bfr(bfr(a * c) + bfr(-b * s));
+      v[h * HD + i + HD / 2] = bfr(bfr(b * c) + bfr(a * s));
+    }
+  }
+}
+
+template <int EPI, int HD>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+            EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES; // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blocks = (M + BM - 1) / BM;
+  const int n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blocks) * BM;
+        const int n0 = (tile % n_blocks) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
+          tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], kb * BK, m0);
+          tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE), 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * B_STAGE), 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_blocks) * BM;
+      const int n0 = (tile % n_blocks) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+
+      // per-row rotary constants, shared by every head in this tile
+      uint32_t cs[(EPI == ESMK_EPI_QKV_ROPE) ? HD / 2 : 1];
+      if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
+        if (n0 < ep.rope_cols) {
+          const int p = row_ok ? ep.pos[row] : 0;
+          const uint32_t* c32 = reinterpret_cast<const uint32_t*>(ep.cosb + (size_t)p * HD);
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(ep.sinb + (size_t)p * HD);
+#pragma unroll
+          for (int i = 0; i < HD / 4; ++i) {
+            const uint32_t c2 = __ldg(c32 + i), s2 = __ldg(s32 + i);  // two consecutive bf16 each
+            cs[2 * i] = (c2 & 0xffffu) | (s2 << 16);
+            cs[2 * i + 1] = (c2 >> 16) | (s2 & 0xffff0000u);
+          }
+        }
+      }
+
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+
+#pragma unroll 1
+      for (int g = 0; g < BN / 64; ++g) {
+        const int col0 = n0 + g * 64;
+        float v[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + g * 64, r0);
+          tmem_ld32(t_row + g * 64 + 32, r1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+        }
+        if (g == BN / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (col0 >= N) continue;
+
+        // ---- bias, first rounding point: bf(A W^T + b) ----
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            const int c = col0 + j;
+            float b0 = 0.f, b1 = 0.f;
+            if (c + 1 < N) {
+              const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t*>(ep.bias + c) );
+              b0 = bf16_lo(b2); b1 = bf16_hi(b2);
+            } else if (c < N) {
+              b0 = __bfloat162float(ep.bias[c]);
+            }
+            v[j] += b0; v[j + 1] += b1;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = bfr(v[j]);
+
+        if constexpr (EPI == ESMK_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
+          if (col0 < ep.rope_cols) rope64<HD>(v, cs);
+        }
+
+        if constexpr (EPI == ESMK_EPI_SWIGLU) {
+          // columns [0,32) = activation rows, [32,64) = the matching fc rows
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = v[j];
+            const float sl = bfr(a / (1.0f + expf(-a)));
+            o[j] = sl * v[32 + j];
+          }
+          if (row_ok) {
+            const int oc0 = col0 >> 1;
+            const int No = N >> 1;
+            __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + oc0;
+            if (ep.vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (oc0 + j < No)
+                  *reinterpret_cast<uint4*>(dst + j) =
+                      make_uint4(pack_bf16(o[j], o[j + 1]), pack_bf16(o[j + 2], o[j + 3]),
+                                 pack_bf16(o[j + 4], o[j + 5]), pack_bf16(o[j + 6], o[j + 7]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (oc0 + j < No) dst[j] = __float2bfloat16_rn(o[j]);
+            }
+          }
+          continue;
+        }
+
+        if (!row_ok) continue;
+        __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + col0;
+        if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+          const __nv_bfloat16* rsd = ep.R + (size_t)row * ep.ldr + col0;
+          if (ep.vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+              if (col0 + j < N) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rsd + j);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  v[j + 2 * q] = bf16_lo(w[q]) + bfr(v[j + 2 * q] / ep.scale);
+                  v[j + 2 * q + 1] = bf16_hi(w[q]) + bfr(v[j + 2 * q + 1] / ep.scale);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < N) v[j] = __bfloat162float(rsd[j]) + bfr(v[j] / ep.scale);
+          }
+        }
+        if (ep.vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 8) {
+            if (col0 + j < N)
+              *reinterpret_cast<uint4*>(dst + j) =
+                  make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                             pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j < N) dst[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int EPI, int HD>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep,
+           cudaStream_t st) {
+  auto kern = gemm_kernel<EPI, HD>;
+  static bool configured = false;
+  if (!configured) {
+    ESMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm(const esmk_gemm_args& a, cudaStream_t st) {
+  ESMK_REQUIRE(a.M >= 0 && a.N >= 1 && a.K >= 1, "bad GEMM shape");
+  ESMK_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0, "GEMM needs K and lda to be multiples of 8 (16-byte TMA pitch)");
+  if (a.M == 0) return 0;
+  CUtensorMap tmA, tmB;
+  ESMK_TRY(make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, BM, BK, 128));
+  ESMK_TRY(make_tmap_2d(&tmB, a.W, a.N, a.K, a.K, BN, BK, 128));
+  EpiParams ep{};
+  ep.C = (__nv_bfloat16*)a.C;
+  ep.ldc = a.ldc;
+  ep.bias = (const __nv_bfloat16*)a.bias;
+  ep.R = (const __nv_bfloat16*)a.R;
+  ep.ldr = a.ldr;
+  ep.scale = a.residue_scaling;
+  ep.cosb = (const __nv_bfloat16*)a.rope_cos;
+  ep.sinb = (const __nv_bfloat16*)a.rope_sin;
+  ep.pos = a.pos;
+  ep.rope_cols = a.rope_cols;
+  const int n_out = a.epilogue == ESMK_EPI_SWIGLU ? a.N / 2 : a.N;
+  ep.vec_ok = (n_out % 8 == 0) && (a.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
+  if (a.bias != nullptr) ESMK_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 3) == 0, "bias must be 4-byte aligned");
+  switch (a.epilogue) {
+    case ESMK_EPI_BIAS:
+      return launch<ESMK_EPI_BIAS, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+    case ESMK_EPI_BIAS_GELU:
+      return launch<ESMK_EPI_BIAS_GELU, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+    case ESMK_EPI_RESIDUAL:
+      ESMK_REQUIRE(a.R != nullptr && a.residue_scaling != 0.f, "residual epilogue needs R and a non-zero scale");
+      ep.vec_ok = ep.vec_ok && (a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+      return launch<ESMK_EPI_RESIDUAL, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+    case ESMK_EPI_SWIGLU:
+      ESMK_REQUIRE(a.N % 64 == 0, "SwiGLU epilogue needs N (= 2F) to be a multiple of 64");
+      ESMK_REQUIRE(a.bias == nullptr, "SwiGLU epilogue has no bias (ESMC linears are bias-free)");
+      return launch<ESMK_EPI_SWIGLU, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+    case ESMK_EPI_QKV_ROPE:
+      ESMK_REQUIRE(a.rope_cos && a.rope_sin && a.pos, "QKV_ROPE epilogue needs cos/sin tables and positions");
+      ESMK_REQUIRE(a.rope_cols % 64 == 0 && a.rope_cols <= a.N, "rope_cols must be a multiple of 64 and <= N");
+      if (a.head_dim == 64) return launch<ESMK_EPI_QKV_ROPE, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 32) return launch<ESMK_EPI_QKV_ROPE, 32>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 16) return launch<ESMK_EPI_QKV_ROPE, 16>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return fail("esmk_gemm", "fused QKV_ROPE supports head_dim 16/32/64; use ESMK_EPI_BIAS + esmk_qk_norm_rope");
+    default:
+      return fail("esmk_gemm", "unknown epilogue");
+  }
+}
+
+}  // namespace esmk

@@ -1,0 +1,182 @@
+// Whole-model driver: the packed forward pass as a fixed sequence of esmk kernels
+// on one stream (no host synchronisation, CUDA-graph capturable).  Replaces the
+// Python layer loop of esme/esm.py:229-252 and the head of esme/head.py:25-27.
+#include <vector>
+
+#include "common.cuh"
+#include "esmk_internal.h"
+
+struct esmk_model {
+  esmk_config cfg;
+  esmk_weights w;
+  std::vector<esmk_layer_weights> layers;
+};
+
+namespace esmk {
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Workspace(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(count * sizeof(T));
+    return p;
+  }
+};
+
+struct Buffers {
+  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb;
+  int32_t *pos, *tile_cu;
+  size_t bytes;
+};
+
+Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len) {
+  Workspace w(ws);
+  Buffers b;
+  const size_t D = c.embed_dim, F = c.ffn_dim, hd = c.embed_dim / c.attention_heads;
+  b.x = w.take<__nv_bfloat16>((size_t)T * D);
+  b.h = w.take<__nv_bfloat16>((size_t)T * D);
+  b.qkv = w.take<__nv_bfloat16>((size_t)T * 3 * D);
+  b.a = w.take<__nv_bfloat16>((size_t)T * D);
+  b.u = w.take<__nv_bfloat16>((size_t)T * F);
+  b.cosb = w.take<__nv_bfloat16>((size_t)max_len * hd);
+  b.sinb = w.take<__nv_bfloat16>((size_t)max_len * hd);
+  b.pos = w.take<int32_t>((size_t)T);
+  b.tile_cu = w.take<int32_t>((size_t)B + 1);
+  b.bytes = w.off;
+  return b;
+}
+
+int linear(const void* A, int lda, const void* W, const void* bias, void* C, int ldc, int M, int N, int K, int epi,
+           cudaStream_t st, const void* R = nullptr, int ldr = 0, float scale = 1.f) {
+  esmk_gemm_args g{};
+  g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.epilogue = epi; g.R = R; g.ldr = ldr; g.residue_scaling = scale;
+  return gemm(g, st);
+}
+
+int head_and_output(const esmk_model* m, const __nv_bfloat16* z, int T, __nv_bfloat16* t0, __nv_bfloat16* t1,
+                    int kind, void* out, cudaStream_t st) {
+  const esmk_config& c = m->cfg;
+  const int D = c.embed_dim, V = c.vocab;
+  // esme/head.py:25-27: final(LN(gelu(dense(x))))
+  ESMK_TRY(linear(z, D, m->w.head_dense_w, m->w.head_dense_b, t0, D, T, D, D, ESMK_EPI_BIAS_GELU, st));
+  ESMK_TRY(layernorm(t0, D, m->w.head_norm_w, m->w.head_norm_b, t1, D, T, D, 1e-5f, st));
+  ESMK_TRY(linear(t1, D, m->w.head_final_w, m->w.head_final_b, out, V, T, V, D, ESMK_EPI_BIAS, st));
+  if (kind == ESMK_OUT_LOG_PROB) ESMK_TRY(softmax(out, V, out, V, T, V, 1, st));
+  if (kind == ESMK_OUT_PROB) ESMK_TRY(softmax(out, V, out, V, T, V, 0, st));
+  return 0;
+}
+
+}  // namespace
+
+int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out) {
+  ESMK_REQUIRE(cfg && w && out, "null argument");
+  ESMK_REQUIRE(cfg->family == 0 || cfg->family == 1, "family must be 0 (ESM2) or 1 (ESMC)");
+  ESMK_REQUIRE(cfg->num_layers >= 1 && cfg->embed_dim >= 8 && cfg->attention_heads >= 1, "bad model dims");
+  ESMK_REQUIRE(cfg->embed_dim % cfg->attention_heads == 0, "embed_dim must be divisible by attention_heads");
+  ESMK_REQUIRE(cfg->embed_dim % 8 == 0 && cfg->ffn_dim % 8 == 0, "embed_dim / ffn_dim must be multiples of 8");
+  const int hd = cfg->embed_dim / cfg->attention_heads;
+  ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "head_dim must be 16, 32, 64 or 128");
+  ESMK_REQUIRE(cfg->vocab >= 1 && cfg->vocab <= 128 && cfg->embed_rows >= cfg->vocab - 0, "bad vocab");
+  ESMK_REQUIRE(cfg->residue_scaling > 0.f, "residue_scaling must be positive");
+  if (cfg->family == 1) ESMK_REQUIRE(cfg->ffn_dim % 32 == 0, "ESMC ffn_dim must be a multiple of 32");
+  ESMK_REQUIRE(w->embed && w->layers && w->final_norm_w && w->head_dense_w && w->head_dense_b && w->head_norm_w &&
+                   w->head_norm_b && w->head_final_w && w->head_final_b,
+               "missing model-level weight");
+  for (int i = 0; i < cfg->num_layers; ++i) {
+    const esmk_layer_weights& l = w->layers[i];
+    ESMK_REQUIRE(l.attn_norm_w && l.attn_norm_b && l.wqkv && l.wo && l.ffn_norm_w && l.ffn_norm_b && l.w1 && l.w2,
+                 "missing layer weight");
+    if (cfg->family == 0) ESMK_REQUIRE(l.bqkv && l.bo && l.b1 && l.b2, "ESM2 layers need biases");
+    if (cfg->family == 1) ESMK_REQUIRE(l.qln_w && l.kln_w, "ESMC layers need QK-LayerNorm weights");
+  }
+  esmk_model* m = new esmk_model();
+  m->cfg = *cfg;
+  m->w = *w;
+  m->layers.assign(w->layers, w->layers + cfg->num_layers);
+  m->w.layers = m->layers.data();
+  *out = m;
+  return 0;
+}
+
+size_t workspace_bytes(const esmk_model* m, int T, int B, int max_len) {
+  return carve(m->cfg, nullptr, T, B, max_len).bytes + 1024;
+}
+
+int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,
+            const uint8_t* zero_rows, void* workspace, size_t workspace_bytes_, int kind, void* out,
+            void* const* layer_taps, cudaStream_t st) {
+  ESMK_REQUIRE(m && tokens && cu_lens && workspace && out, "null argument");
+  ESMK_REQUIRE(T >= 1 && B >= 1 && max_len >= 1, "empty batch");
+  ESMK_REQUIRE(kind >= ESMK_OUT_LOGITS && kind <= ESMK_OUT_REPRESENTATION, "bad output kind");
+  const esmk_config& c = m->cfg;
+  void* ws = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(workspace)));
+  Buffers b = carve(c, ws, T, B, max_len);
+  ESMK_REQUIRE(b.bytes + (static_cast<uint8_t*>(ws) - static_cast<uint8_t*>(workspace)) <= workspace_bytes_,
+               "workspace too small (see esmk_workspace_bytes)");
+  const int D = c.embed_dim, H = c.attention_heads, hd = D / H, F = c.ffn_dim;
+  const float s = c.residue_scaling;
+  const bool fused_rope = (c.family == 0) && (hd <= 64) && ((2 * D) % 64 == 0);
+
+  ESMK_TRY(batch_meta(cu_lens, B, T, b.pos, b.tile_cu, st));
+  ESMK_TRY(rope_tables(b.cosb, b.sinb, max_len, hd, st));
+  // esme/esm.py:188-189: ESM2 zeroes <mask>(32) rows; ESMC (esm.py:876) does not
+  ESMK_TRY(embed(tokens, m->w.embed, b.x, T, D, c.embed_rows, c.family == 0 ? 32 : -1, zero_rows, st));
+
+  for (int i = 0; i < c.num_layers; ++i) {
+    const esmk_layer_weights& l = m->layers[i];
+    // ---- attention block: x = x + out(attn(rope(qkv(LN(x))))) / s   (esme/attention.py:126-139, 253-254)
+    ESMK_TRY(layernorm(b.x, D, l.attn_norm_w, l.attn_norm_b, b.h, D, T, D, 1e-5f, st));
+    if (fused_rope) {
+      esmk_gemm_args g{};
+      g.A = b.h; g.lda = D; g.W = l.wqkv; g.bias = l.bqkv; g.C = b.qkv; g.ldc = 3 * D;
+      g.M = T; g.N = 3 * D; g.K = D; g.epilogue = ESMK_EPI_QKV_ROPE;
+      g.rope_cos = b.cosb; g.rope_sin = b.sinb; g.pos = b.pos; g.head_dim = hd; g.rope_cols = 2 * D;
+      ESMK_TRY(gemm(g, st));
+    } else {
+      ESMK_TRY(linear(b.h, D, l.wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
+      ESMK_TRY(qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
+    }
+    ESMK_TRY(attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_cu, B, T, H, hd, max_len, 0,
+                         st));
+    ESMK_TRY(linear(b.a, D, l.wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)
+    ESMK_TRY(layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));
+    if (c.family == 0) {
+      ESMK_TRY(linear(b.h, D, l.w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
+    } else {
+      ESMK_TRY(linear(b.h, D, l.w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
+    }
+    ESMK_TRY(linear(b.u, F, l.w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    if (layer_taps != nullptr && layer_taps[i] != nullptr)
+      ESMK_CUDA(cudaMemcpyAsync(layer_taps[i], b.x, (size_t)T * D * 2, cudaMemcpyDeviceToDevice, st));
+  }
+  // esme/esm.py:252
+  if (kind == ESMK_OUT_REPRESENTATION)
+    return layernorm(b.x, D, m->w.final_norm_w, m->w.final_norm_b, out, D, T, D, 1e-5f, st);
+  ESMK_TRY(layernorm(b.x, D, m->w.final_norm_w, m->w.final_norm_b, b.h, D, T, D, 1e-5f, st));
+  return head_and_output(m, b.h, T, b.a, b.x, kind, out, st);
+}
+
+int lm_head(esmk_model* m, const void* x, int T, void* workspace, size_t workspace_bytes_, int kind, void* out,
+            cudaStream_t st) {
+  ESMK_REQUIRE(m && x && workspace && out, "null argument");
+  ESMK_REQUIRE(kind >= ESMK_OUT_LOGITS && kind <= ESMK_OUT_PROB, "bad output kind");
+  if (T == 0) return 0;
+  const size_t D = m->cfg.embed_dim;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace)));
+  const size_t one = align_up((size_t)T * D * 2);
+  ESMK_REQUIRE((size_t)(ws - static_cast<uint8_t*>(workspace)) + 2 * one <= workspace_bytes_,
+               "workspace too small: need 2*T*D*2 + 3072 bytes");
+  return head_and_output(m, static_cast<const __nv_bfloat16*>(x), T, reinterpret_cast<__nv_bfloat16*>(ws),
+                         reinterpret_cast<__nv_bfloat16*>(ws + one), kind, out, st);
+}
+
+}  // namespace esmk

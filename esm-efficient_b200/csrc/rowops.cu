@@ -1,0 +1,358 @@
+// Row-wise (HBM-bound) operators: batch metadata, RoPE tables, embedding gather,
+// LayerNorm, QK-LayerNorm + RoPE, (log-)softmax.  One warp per row, 16-byte
+// vector loads/stores, fp32 statistics, bf16 I/O with the reference's rounding
+// points.
+#include "common.cuh"
+#include "esmk_internal.h"
+
+namespace esmk {
+
+constexpr int kRowWarps = 8;  // warps (rows) per CTA
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------
+// batch metadata
+// ---------------------------------------------------------------------------
+__global__ void batch_meta_kernel(const int32_t* __restrict__ cu, int B, int T, int32_t* __restrict__ pos,
+                                  int32_t* __restrict__ tile_cu) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 && tile_cu != nullptr) {
+    int acc = 0;
+    tile_cu[0] = 0;
+    for (int s = 0; s < B; ++s) {
+      acc += (cu[s + 1] - cu[s] + 127) >> 7;
+      tile_cu[s + 1] = acc;
+    }
+  }
+  if (t < T && pos != nullptr) {
+    int lo = 0, hi = B;  // find s with cu[s] <= t < cu[s+1]
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (cu[mid] <= t) lo = mid; else hi = mid;
+    }
+    pos[t] = t - cu[lo];
+  }
+}
+
+int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, cudaStream_t st) {
+  ESMK_REQUIRE(B >= 1 && T >= 1, "empty batch");
+  int threads = 256;
+  batch_meta_kernel<<<(T + threads - 1) / threads, threads, 0, st>>>(cu_lens, B, T, pos, tile_cu);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// RoPE tables (esme/rotary.py:116-149): fp32 everywhere, one final cast to bf16
+// ---------------------------------------------------------------------------
+__global__ void rope_tables_kernel(__nv_bfloat16* __restrict__ cosb, __nv_bfloat16* __restrict__ sinb, int max_len,
+                                   int hd) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int half = hd / 2;
+  if (idx >= max_len * half) return;
+  int p = idx / half, i = idx % half;
+  // inv_freq = 1 / (10000 ** (2i / hd)) with fp32 pow and fp32 division, like torch
+  float expo = (float)(2 * i) / (float)hd;
+  float inv_freq = 1.0f / powf(10000.0f, expo);
+  float ang = (float)p * inv_freq;
+  __nv_bfloat16 c = __float2bfloat16_rn(cosf(ang));
+  __nv_bfloat16 s = __float2bfloat16_rn(sinf(ang));
+  cosb[(size_t)p * hd + i] = c;
+  cosb[(size_t)p * hd + i + half] = c;
+  sinb[(size_t)p * hd + i] = s;
+  sinb[(size_t)p * hd + i + half] = s;
+}
+
+int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st) {
+  ESMK_REQUIRE(max_len >= 1 && hd >= 2 && hd % 2 == 0, "bad rope table shape");
+  int n = max_len * (hd / 2);
+  rope_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>((__nv_bfloat16*)cosb, (__nv_bfloat16*)sinb, max_len, hd);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// embedding gather
+// ---------------------------------------------------------------------------
+__global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint4* __restrict__ table,
+                             uint4* __restrict__ out, int T, int D8, int vocab, int zero_token,
+                             const uint8_t* __restrict__ zero_rows) {
+  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  long long tok = tokens[row];
+  bool zero = (tok == zero_token) || (zero_rows != nullptr && zero_rows[row] != 0) || tok < 0 || tok >= vocab;
+  const uint4* src = table + (size_t)(zero ? 0 : tok) * D8;
+  uint4* dst = out + (size_t)row * D8;
+  for (int c = lane; c < D8; c += 32) dst[c] = zero ? make_uint4(0, 0, 0, 0) : __ldg(src + c);
+}
+
+int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
+          const uint8_t* zero_rows, cudaStream_t st) {
+  ESMK_REQUIRE(D % 8 == 0, "embed_dim must be a multiple of 8");
+  embed_kernel<<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+      tokens, (const uint4*)table, (uint4*)out, T, D / 8, vocab, zero_token, zero_rows);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm.  NCH = uint4 chunks held per lane (row fits in registers for
+// D <= NCH*256); exact two-pass statistics in fp32.
+// ---------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kRowWarps * 32)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ w,
+                 const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, int ldy, int T, int D,
+                 float eps) {
+  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
+  const int D8 = D >> 3;
+  float v[NCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int idx = c * 32 + lane;
+    if (idx < D8) {
+      uint4 u = xr[idx];
+      unpack8(u, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c * 32 + lane < D8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float d = v[c][j] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * ldy);
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  const uint4* b4 = reinterpret_cast<const uint4*>(b);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int idx = c * 32 + lane;
+    if (idx < D8) {
+      float wf[8], bf[8], o[8];
+      unpack8(__ldg(w4 + idx), wf);
+      if (b != nullptr) unpack8(__ldg(b4 + idx), bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float n = (v[c][j] - mean) * rstd * wf[j];
+        o[j] = (b != nullptr) ? n + bf[j] : n;
+      }
+      yr[idx] = pack8(o);
+    }
+  }
+}
+
+template <int NCH>
+static void launch_ln(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
+                      cudaStream_t st) {
+  layernorm_kernel<NCH><<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, T, D,
+      eps);
+}
+
+int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
+              cudaStream_t st) {
+  ESMK_REQUIRE(D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "LayerNorm needs D and pitches to be multiples of 8");
+  ESMK_REQUIRE(D <= 20 * 256, "LayerNorm supports D <= 5120");
+  if (T == 0) return 0;
+  int nch = (D + 255) / 256;
+  if (nch <= 1) launch_ln<1>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else if (nch <= 2) launch_ln<2>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else if (nch <= 4) launch_ln<4>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else if (nch <= 5) launch_ln<5>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else if (nch <= 8) launch_ln<8>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else if (nch <= 10) launch_ln<10>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  else launch_ln<20>(x, ldx, w, b, y, ldy, T, D, eps, st);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (QK-LayerNorm) + RoPE on packed q and k rows, in place.
+// blockIdx.y selects q (0) or k (1).  hd in {16,32,64,128}: the rotation partner
+// of a lane's 8 elements lives hd/16 lanes away in the same register slot.
+// ---------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kRowWarps * 32)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int ld, int T, int D, int hd,
+                    const __nv_bfloat16* __restrict__ lnq, const __nv_bfloat16* __restrict__ lnk,
+                    const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
+                    const int32_t* __restrict__ pos) {
+  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  __nv_bfloat16* base = (blockIdx.y == 0 ? q : k) + (size_t)row * ld;
+  const __nv_bfloat16* lnw = blockIdx.y == 0 ? lnq : lnk;
+  uint4* xr = reinterpret_cast<uint4*>(base);
+  const int D8 = D >> 3;
+  float v[NCH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int idx = c * 32 + lane;
+    if (idx < D8) {
+      unpack8(xr[idx], v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+  if (lnw != nullptr) {  // ESMC: q = bf(LN_w(q)) over the full embedding dim
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (c * 32 + lane < D8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float d = v[c][j] - mean; sq += d * d; }
+      }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + 1e-5f);
+    const uint4* w4 = reinterpret_cast<const uint4*>(lnw);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      int idx = c * 32 + lane;
+      if (idx < D8) {
+        float wf[8];
+        unpack8(__ldg(w4 + idx), wf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c][j] = bfr((v[c][j] - mean) * rstd * wf[j]);
+      }
+    }
+  }
+  if (cosb != nullptr) {
+    const int p = pos[row];
+    const int half = hd >> 1;
+    const int lane_xor = hd >> 4;  // partner lane distance: (hd/2)/8
+    const uint4* c4 = reinterpret_cast<const uint4*>(cosb + (size_t)p * hd);
+    const uint4* s4 = reinterpret_cast<const uint4*>(sinb + (size_t)p * hd);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      int idx = c * 32 + lane;
+      int o = (idx * 8) % hd;  // offset of this 8-element group inside its head
+      float cf[8], sf[8];
+      if (idx < D8) {
+        unpack8(__ldg(c4 + (o >> 3)), cf);
+        unpack8(__ldg(s4 + (o >> 3)), sf);
+      }
+      const float sign = (o < half) ? -1.f : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float partner = __shfl_xor_sync(0xffffffffu, v[c][j], lane_xor);
+        if (idx < D8) v[c][j] = bfr(bfr(v[c][j] * cf[j]) + bfr(sign * partner * sf[j]));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    int idx = c * 32 + lane;
+    if (idx < D8) xr[idx] = pack8(v[c]);
+  }
+}
+
+template <int NCH>
+static void launch_qk(void* q, void* k, int ld, int T, int D, int hd, const void* lnq, const void* lnk,
+                      const void* cosb, const void* sinb, const int32_t* pos, cudaStream_t st) {
+  dim3 grid((T + kRowWarps - 1) / kRowWarps, 2);
+  qk_norm_rope_kernel<NCH><<<grid, kRowWarps * 32, 0, st>>>(
+      (__nv_bfloat16*)q, (__nv_bfloat16*)k, ld, T, D, hd, (const __nv_bfloat16*)lnq, (const __nv_bfloat16*)lnk,
+      (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, pos);
+}
+
+int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,
+                 const void* sinb, const int32_t* pos, cudaStream_t st) {
+  const int D = H * hd;
+  ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "rotary head_dim must be 16, 32, 64 or 128");
+  ESMK_REQUIRE(ld % 8 == 0 && D <= 20 * 256, "bad q/k pitch or embed_dim > 5120");
+  ESMK_REQUIRE((cosb == nullptr) == (sinb == nullptr), "cos and sin must be given together");
+  ESMK_REQUIRE(cosb == nullptr || pos != nullptr, "positions required for rotary");
+  if (T == 0) return 0;
+  int nch = (D + 255) / 256;
+  if (nch <= 1) launch_qk<1>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  else if (nch <= 2) launch_qk<2>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  else if (nch <= 4) launch_qk<4>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  else if (nch <= 5) launch_qk<5>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  else if (nch <= 10) launch_qk<10>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  else launch_qk<20>(q, k, ld, T, D, hd, lnq, lnk, cosb, sinb, pos, st);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (log-)softmax over a short last dim (V <= 128): one warp per row
+// ---------------------------------------------------------------------------
+__global__ void softmax_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
+                               int T, int V, int log_mode) {
+  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  float v[4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = lane + 32 * i;
+    v[i] = c < V ? __bfloat162float(xr[c]) : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += (lane + 32 * i < V) ? expf(v[i] - m) : 0.f;
+  s = warp_sum(s);
+  const float lse = logf(s);
+  __nv_bfloat16* yr = y + (size_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = lane + 32 * i;
+    if (c < V) yr[c] = __float2bfloat16_rn(log_mode ? (v[i] - m - lse) : expf(v[i] - m) / s);
+  }
+}
+
+int softmax(const void* x, int ldx, void* y, int ldy, int T, int V, int log_mode, cudaStream_t st) {
+  ESMK_REQUIRE(V >= 1 && V <= 128, "softmax supports 1 <= V <= 128");
+  if (T == 0) return 0;
+  softmax_kernel<<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, T, V, log_mode);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace esmk

@@ -1,0 +1,76 @@
+// Host utilities: thread-local error string, TMA tensor-map encoding through the
+// driver entry point (no link-time libcuda dependency), device properties.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace esmk {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+int fail(const char* where, const std::string& msg) {
+  g_last_error = std::string(where) + ": " + msg;
+  return 1;
+}
+
+int check_cuda(cudaError_t e, const char* where) {
+  if (e == cudaSuccess) return 0;
+  g_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return 2;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  ESMK_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  ESMK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  ESMK_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  ESMK_REQUIRE(box_rows <= 256 && box_cols <= 256, "TMA box dims must be <= 256");
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else ESMK_REQUIRE(swizzle_bytes == 0, "bad swizzle");
+  if (swizzle_bytes) ESMK_REQUIRE(box_cols * 2 == (uint32_t)swizzle_bytes, "box inner bytes must equal swizzle span");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled", "CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace esmk

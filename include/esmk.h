@@ -1,0 +1,184 @@
+/* esmk.h -- C ABI of libesmk.so, the sm_100a (B200) kernels behind the `esme`
+ * drop-in for the ESM inference forward pass.
+ *
+ * Conventions
+ *   - Every entry point returns 0 on success, non-zero on error; the message
+ *     is available (thread-local) through esmk_last_error().  Nothing throws
+ *     across the ABI.
+ *   - All tensor pointers are DEVICE pointers to row-major bf16 unless stated;
+ *     `ld*` are row pitches in ELEMENTS.  `stream` is a cudaStream_t.
+ *   - The caller allocates every output and workspace; the library owns no
+ *     tensor memory (esmk_model_t only keeps the pointers it was given plus
+ *     pre-encoded TMA descriptors).  Calls are asynchronous on `stream`.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with a CUDA error.
+ *
+ * Each function cites the reference (`/root/reference`, package `esme`)
+ * operator it replaces.
+ */
+#ifndef ESMK_H
+#define ESMK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ESMK_API __attribute__((visibility("default")))
+#else
+#define ESMK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* esmk_stream_t; /* cudaStream_t */
+
+/* ---- library ----------------------------------------------------------- */
+ESMK_API const char* esmk_last_error(void);
+ESMK_API int esmk_version(void);
+/* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
+ESMK_API uint64_t esmk_launch_count(void);
+
+/* ---- batch metadata ---------------------------------------------------- */
+/* Per-token position inside its own sequence and q-tile prefix sums.
+ * Replaces esme/rotary.py:5-14 `culen_indices` (which the reference recomputes,
+ * with host syncs, twice per layer); computed once per batch here.
+ *   cu_lens  int32[B+1]          (device)
+ *   pos      int32[T]            out: t - cu_lens[seq(t)]
+ *   tile_cu  int32[B+1]          out: prefix sum of ceil(L_s / 128) (attention work list) */
+ESMK_API int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, esmk_stream_t stream);
+
+/* cos/sin tables, esme/rotary.py:116-149: fp32 angle = p * 10000^(-2i/hd), table row = [f, f],
+ * cast to bf16.  cos, sin: bf16 [max_len, hd]. */
+ESMK_API int esmk_rope_tables(void* cos, void* sin, int max_len, int head_dim, esmk_stream_t stream);
+
+/* ---- row-wise operators ------------------------------------------------ */
+/* esme/esm.py:176-199 (ESM2.embedding) / esme/esm.py:876 (ESMC): out[t] = table[tokens[t]];
+ * rows whose token == zero_token (ESM2: <mask>=32, ESMC: -1 = none) or whose
+ * zero_rows[t] != 0 (optional uint8[T], e.g. pad rows of the 2-D entry) are zero. */
+ESMK_API int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
+               const uint8_t* zero_rows, esmk_stream_t stream);
+
+/* torch.nn.LayerNorm over the last dim (eps, biased variance, fp32 statistics, bf16 in/out):
+ * esme/attention.py:92, 222|230; esme/esm.py:252; esme/head.py:26.  bias may be NULL. */
+ESMK_API int esmk_layernorm(const void* x, int ldx, const void* weight, const void* bias, void* y, int ldy, int T, int D,
+                   float eps, esmk_stream_t stream);
+
+/* esme/rotary.py:22-43 `apply_rotary` on packed [T,H,hd] q and k (in place allowed):
+ * out = bf(bf(x*cos[pos]) + bf(rotate_half(x)*sin[pos])).  If ln_q_weight/ln_k_weight are
+ * non-NULL the ESMC QK-LayerNorm over the full D = H*hd (weight only, eps 1e-5;
+ * esme/attention.py:104-105) is applied first.  cos/sin may be NULL to skip the rotation. */
+ESMK_API int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_dim, const void* ln_q_weight,
+                      const void* ln_k_weight, const void* cos, const void* sin, const int32_t* pos,
+                      esmk_stream_t stream);
+
+/* esme/esm.py:297,317: (log_)softmax over the last dim of bf16 logits [T,V], bf16 out. */
+ESMK_API int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t stream);
+
+/* ---- GEMM family (tcgen05 + TMA) ---------------------------------------- */
+enum esmk_epilogue {
+  ESMK_EPI_BIAS = 0,      /* C = bf(A W^T + b)                       nn.Linear                         */
+  ESMK_EPI_BIAS_GELU = 1, /* C = bf(gelu_erf(bf(A W^T + b)))          attention.py:231-233, head.py:26   */
+  ESMK_EPI_RESIDUAL = 2,  /* C = bf(R + bf(bf(A W^T + b) / s))        attention.py:139,253-255           */
+  ESMK_EPI_QKV_ROPE = 3,  /* C = [rope(q) | rope(k) | v], W = [Wq;Wk;Wv]  attention.py:102 + rotary.py:43 */
+  ESMK_EPI_SWIGLU = 4     /* C = bf(bf(silu(bf(a))) * bf(f)), W rows interleaved in blocks of 32
+                             (32 `activation` rows, then the 32 matching `fc` rows)  attention.py:281   */
+};
+
+typedef struct {
+  const void* A;  /* [M,K] activations */
+  int lda;
+  const void* W;  /* [N,K] weight, nn.Linear layout (row pitch K) */
+  const void* bias; /* [N] or NULL */
+  void* C;        /* [M,N] (SWIGLU: [M,N/2]) */
+  int ldc;
+  int M, N, K;
+  int epilogue;   /* enum esmk_epilogue */
+  /* RESIDUAL */
+  const void* R;  /* [M,N] residual (may alias C) */
+  int ldr;
+  float residue_scaling; /* s (divides, as the reference does) */
+  /* QKV_ROPE */
+  const void* rope_cos; /* bf16 [max_len, hd] */
+  const void* rope_sin;
+  const int32_t* pos;   /* int32 [M] */
+  int head_dim;         /* 16, 32, 64 or 128 */
+  int rope_cols;        /* columns [0, rope_cols) are rotated (= 2*D) */
+} esmk_gemm_args;
+
+ESMK_API int esmk_gemm(const esmk_gemm_args* args, esmk_stream_t stream);
+
+/* ---- variable-length multi-head attention -------------------------------- */
+/* Replaces flash_attn_varlen_func as called at esme/attention.py:115-123:
+ * per sequence s and head h, O = softmax(Q K^T * hd^-0.5) V, non-causal, no dropout,
+ * fp32 scores / accumulation, P rounded to bf16 before P V.
+ *   q,k,v : bf16, token t / head h at  ptr + t*ld + h*hd   (e.g. three column
+ *           blocks of one [T,3D] QKV GEMM output, ld = 3D)
+ *   out   : bf16 [T, H*hd], pitch ldo
+ *   tile_cu from esmk_batch_meta.
+ * head_dim == 64 runs the tcgen05/TMA kernel; other head dims (<=128, multiple of 8)
+ * run a CUDA-core kernel.  impl: 0 = auto, 1 = force the CUDA-core kernel. */
+ESMK_API int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo,
+                     const int32_t* cu_lens, const int32_t* tile_cu, int B, int T, int H, int head_dim,
+                     int max_len, int impl, esmk_stream_t stream);
+
+/* ---- whole model --------------------------------------------------------- */
+typedef struct {
+  int family;          /* 0 = ESM2 (bias, GELU FFN, mask-row zeroing), 1 = ESMC (QK-LN, SwiGLU, residue scaling) */
+  int num_layers, embed_dim, attention_heads, ffn_dim, vocab, embed_rows;
+  float residue_scaling;
+} esmk_config;
+
+typedef struct {
+  const void *attn_norm_w, *attn_norm_b;
+  const void *wqkv, *bqkv;       /* [3D,D], [3D] or NULL */
+  const void *qln_w, *kln_w;     /* ESMC only, else NULL */
+  const void *wo, *bo;           /* [D,D] */
+  const void *ffn_norm_w, *ffn_norm_b;
+  const void *w1, *b1;           /* ESM2 [F,D]; ESMC interleaved [2F,D] */
+  const void *w2, *b2;           /* [D,F] */
+} esmk_layer_weights;
+
+typedef struct {
+  const void* embed;                      /* [embed_rows, D] */
+  const esmk_layer_weights* layers;       /* host array [num_layers] */
+  const void *final_norm_w, *final_norm_b;
+  const void *head_dense_w, *head_dense_b;
+  const void *head_norm_w, *head_norm_b;
+  const void *head_final_w, *head_final_b; /* [V,D], [V] */
+} esmk_weights;
+
+typedef struct esmk_model esmk_model_t;
+
+ESMK_API int esmk_model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model_t** out);
+ESMK_API void esmk_model_destroy(esmk_model_t* m);
+/* bytes of scratch esmk_forward needs for a T-token, B-sequence batch with the given max_len */
+ESMK_API size_t esmk_workspace_bytes(const esmk_model_t* m, int T, int B, int max_len);
+
+enum esmk_output {
+  ESMK_OUT_LOGITS = 0,        /* [T,V]  ESM2.forward                esme/esm.py:268-282 */
+  ESMK_OUT_LOG_PROB = 1,      /* [T,V]  predict_log_prob            esme/esm.py:284-298 */
+  ESMK_OUT_PROB = 2,          /* [T,V]  predict_prob                esme/esm.py:300-317 */
+  ESMK_OUT_REPRESENTATION = 3 /* [T,D]  forward_representation      esme/esm.py:201-266 */
+};
+
+/* The packed forward: embedding -> layers -> final LN -> (LM head -> (log_)softmax).
+ * Replaces the loop at esme/esm.py:229-252 (+ head.py:25-27).
+ *   tokens int64[T], cu_lens int32[B+1] (device), zero_rows optional uint8[T]
+ *   out: bf16 [T,V] or [T,D] (dense, pitch V or D)
+ *   layer_taps: optional host array of num_layers device pointers (or NULL entries);
+ *               layer i's output x [T,D] is copied there (forward_representation(layers=[...])). */
+ESMK_API int esmk_forward(esmk_model_t* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,
+                 const uint8_t* zero_rows, void* workspace, size_t workspace_bytes, int output_kind, void* out,
+                 void* const* layer_taps, esmk_stream_t stream);
+
+/* LM head alone on arbitrary rows (the padded entry runs it on pad rows too, esme/esm.py:281):
+ * x [T,D] -> out [T,V]; workspace >= 2*T*D*2 bytes. */
+ESMK_API int esmk_lm_head(esmk_model_t* m, const void* x, int T, void* workspace, size_t workspace_bytes, int output_kind,
+                 void* out, esmk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESMK_H */
