@@ -1,0 +1,355 @@
+"""Model API (drop-in for esme/esm.py of the reference): ESM, ESM2, ESMC with
+from_pretrained / forward / forward_representation / predict_log_prob /
+predict_prob.  The nn.Module tree carries the reference's parameter names; the
+forward pass is one call into libesmk.so (`esmk_forward`), which runs the whole
+layer loop as a fixed kernel sequence on the current CUDA stream."""
+import ctypes as C
+import math
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from safetensors import safe_open
+
+from . import _lib as L
+from . import ops
+from .alphabet import Alphabet, Alphabet3
+from .attention import FlashTransformerLayer, SwiGLU
+from .head import RobertaLMHead
+
+model_names = ['esm2_8m', 'esm2_35m', 'esm2_150m', 'esm2_650m', 'esm2_3b', 'esm2_15b',
+               'esmc_300m', 'esmc_600m', 'esm1b', 'esm1v_1', 'esm1v_2', 'esm1v_3', 'esm1v_4', 'esm1v_5']
+
+
+def _read_metadata(path) -> dict:
+    with safe_open(path, framework='pt', device='cpu') as f:
+        return dict(f.metadata() or {})
+
+
+class ESM(nn.Module):
+    """Family dispatcher (reference: esme/esm.py:28-69)."""
+
+    @staticmethod
+    def from_pretrained(path, quantization=None, checkpointing=False, device='cpu'):
+        if not os.path.isfile(path):
+            # the reference would download `path` from the HF hub here (esme/download.py:25-52); this
+            # build has no network code -- an unknown file is reported with the reference's error type
+            raise ValueError(f'Invalid model name: {path}. Must be a local .safetensors file '
+                             f'(known model names: {model_names})')
+        name = _read_metadata(path)['name'].split('_')[0]
+        if name == 'esm2':
+            return ESM2.from_pretrained(path, quantization, checkpointing, device)
+        if name == 'esmc':
+            return ESMC.from_pretrained(path, quantization, checkpointing, device)
+        if name in ('esm1b', 'esm1v'):
+            raise NotImplementedError(f'{name}: learned-positional-embedding models are outside this build '
+                                      f'(SURVEY.md §2: not in the hot-path scope)')
+        raise ValueError(f'Invalid model name: {name}. Must be one of {model_names}')
+
+
+class _Engine:
+    """Device-side packed weights + esmk_model_t handle for one nn.Module instance."""
+
+    def __init__(self, model: 'ESM2'):
+        self.device = model.embed_tokens.weight.device
+        self.keep: List[torch.Tensor] = []         # packed tensors the handle points into
+        family = 1 if isinstance(model, ESMC) else 0
+        layers = (L.LayerWeights * model.num_layers)()
+        for i, layer in enumerate(model.layers):
+            sa, lw = layer.self_attn, layers[i]
+            wqkv, bqkv = sa.packed_qkv()
+            self.keep += [wqkv] + ([bqkv] if bqkv is not None else [])
+            lw.attn_norm_w, lw.attn_norm_b = sa.norm.weight.data_ptr(), sa.norm.bias.data_ptr()
+            lw.wqkv, lw.bqkv = wqkv.data_ptr(), ops._ptr(bqkv)
+            lw.qln_w = sa.layernorm_q.weight.data_ptr() if sa.pre_layernorm else None
+            lw.kln_w = sa.layernorm_k.weight.data_ptr() if sa.pre_layernorm else None
+            lw.wo, lw.bo = sa.out.weight.data_ptr(), ops._ptr(sa.out.bias)
+            ln = layer.final[0]
+            lw.ffn_norm_w, lw.ffn_norm_b = ln.weight.data_ptr(), ln.bias.data_ptr()
+            if family == 0:
+                up, down = layer.final[1], layer.final[3]
+                lw.w1, lw.b1 = up.weight.data_ptr(), ops._ptr(up.bias)
+            else:
+                glu, down = layer.final[1], layer.final[2]
+                w1 = SwiGLU.interleave(glu.activation.weight.detach(), glu.fc.weight.detach())
+                self.keep.append(w1)
+                lw.w1, lw.b1 = w1.data_ptr(), None
+            lw.w2, lw.b2 = down.weight.data_ptr(), ops._ptr(down.bias)
+        w = L.Weights()
+        w.embed = model.embed_tokens.weight.data_ptr()
+        w.layers = layers
+        fn, hd = model.emb_layer_norm_after, model.lm_head
+        w.final_norm_w, w.final_norm_b = fn.weight.data_ptr(), ops._ptr(fn.bias)
+        w.head_dense_w, w.head_dense_b = hd.dense.weight.data_ptr(), hd.dense.bias.data_ptr()
+        w.head_norm_w, w.head_norm_b = hd.layer_norm.weight.data_ptr(), hd.layer_norm.bias.data_ptr()
+        w.head_final_w, w.head_final_b = hd.final.weight.data_ptr(), hd.final.bias.data_ptr()
+        cfg = L.Config(family, model.num_layers, model.embed_dim, model.attention_heads,
+                       model.layers[0].ffn_dim, hd.final.out_features, model.embed_tokens.num_embeddings,
+                       float(model.layers[0].residue_scaling))
+        self.vocab = hd.final.out_features
+        self.embed_dim = model.embed_dim
+        handle = L.c_void_p()
+        L.check(L.lib.esmk_model_create(C.byref(cfg), C.byref(w), C.byref(handle)), 'esmk_model_create')
+        self.handle = handle
+        self._layers_struct = layers
+        self.workspace: Optional[torch.Tensor] = None
+        self.stamp = _stamp(model)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                L.lib.esmk_model_destroy(self.handle)
+        except Exception:
+            pass
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        if self.workspace is None or self.workspace.numel() < nbytes:
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self.workspace
+
+    def forward(self, tokens, cu_lens, max_len, kind, taps=None) -> torch.Tensor:
+        T, B = tokens.numel(), cu_lens.numel() - 1
+        width = self.embed_dim if kind == L.OUT_REPRESENTATION else self.vocab
+        out = torch.empty(T, width, dtype=torch.bfloat16, device=self.device)
+        ws = self._ws(L.lib.esmk_workspace_bytes(self.handle, T, B, max_len))
+        tap_arr = None
+        if taps:
+            tap_arr = (L.c_void_p * len(self._layers_struct))()
+            for i, t in taps.items():
+                tap_arr[i] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.esmk_forward(self.handle, tokens.data_ptr(), cu_lens.data_ptr(), T, B, int(max_len), None,
+                                       ws.data_ptr(), ws.numel(), kind, out.data_ptr(), tap_arr,
+                                       ops._stream()), 'esmk_forward')
+        return out
+
+    def lm_head(self, x2d: torch.Tensor, kind) -> torch.Tensor:
+        T = x2d.shape[0]
+        out = torch.empty(T, self.vocab, dtype=torch.bfloat16, device=self.device)
+        ws = self._ws(2 * T * self.embed_dim * 2 + 4096)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.esmk_lm_head(self.handle, x2d.data_ptr(), T, ws.data_ptr(), ws.numel(), kind,
+                                       out.data_ptr(), ops._stream()), 'esmk_lm_head')
+        return out
+
+
+def _stamp(model) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+class ESM2(nn.Module):
+    """ESM-2 (reference: esme/esm.py:72-374).  `from_pretrained(path, quantization,
+    checkpointing, device)` and the forward-family methods keep the reference's
+    signatures, shapes, dtypes and error behaviour."""
+
+    _alphabet = Alphabet
+    _vocab = 33
+    _embed_rows = 33
+
+    def __init__(self, num_layers: int = 33, embed_dim: int = 1280, attention_heads: int = 20,
+                 checkpointing: bool = False, rotary_embedding: bool = True, dropout: float = 0.,
+                 dtype=torch.bfloat16):
+        super().__init__()
+        if not rotary_embedding:
+            raise NotImplementedError('ESM2/ESMC always use rotary embeddings')
+        self.num_layers = num_layers
+        self.embed_dim = embed_dim
+        self.attention_heads = attention_heads
+        self.checkpointing = bool(checkpointing)   # activation checkpointing is a training feature: accepted, unused
+        self.embed_scale = 1
+        self.embed_tokens = nn.Embedding(self._embed_rows, embed_dim, dtype=dtype,
+                                         padding_idx=self._alphabet.padding_idx)
+        self.layers = nn.ModuleList(self._make_layer(dropout, dtype) for _ in range(num_layers))
+        self.emb_layer_norm_after = self._make_final_norm(dtype)
+        self.lm_head = RobertaLMHead(embed_dim, self._vocab, dtype=dtype)
+        self._engine: Optional[_Engine] = None
+
+    # ---- architecture hooks (ESMC overrides) --------------------------------
+    def _make_layer(self, dropout, dtype):
+        return FlashTransformerLayer(self.embed_dim, 4, self.attention_heads, rotary_embedding=True,
+                                     pre_layernorm=False, bias=True, final_activation='gelu',
+                                     dropout=dropout, dtype=dtype)
+
+    def _make_final_norm(self, dtype):
+        return nn.LayerNorm(self.embed_dim, dtype=dtype)
+
+    _zero_mask_rows = True      # esme/esm.py:189
+
+    # ---- engine --------------------------------------------------------------
+    def engine(self) -> _Engine:
+        dev = self.embed_tokens.weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError('esme (B200 build) has no CPU path: load the model with device="cuda" '
+                               '(ESM.from_pretrained(path, device="cuda")) or call model.cuda()')
+        if self._engine is None or self._engine.device != dev or self._engine.stamp != _stamp(self):
+            self._engine = _Engine(self)
+        return self._engine
+
+    def _apply(self, fn, *a, **kw):        # .to()/.cuda()/.half() invalidate the packed weights
+        self._engine = None
+        return super()._apply(fn, *a, **kw)
+
+    # ---- reference API -------------------------------------------------------
+    def embedding(self, tokens, pad_args=None):
+        """esme/esm.py:176-199."""
+        if tokens.ndim not in (1, 2):
+            raise ValueError('tokens must be 1D or 2D')
+        zero_rows = tokens.eq(self._alphabet.padding_idx) if tokens.ndim == 2 else None
+        return ops.embed(tokens, self.embed_tokens.weight,
+                         zero_token=self._alphabet.mask_idx if self._zero_mask_rows else -1, zero_rows=zero_rows)
+
+    def _unpad(self, tokens2d):
+        """Packed view of a padded batch (the job of flash_attn.bert_padding.unpad_input
+        at esme/esm.py:238): -> tokens[T], indices[T] into the [B,S] grid, cu_lens int32[B+1], max_len."""
+        keep = tokens2d.ne(self._alphabet.padding_idx)
+        lens = keep.sum(dim=1, dtype=torch.int32)
+        cu_lens = torch.zeros(tokens2d.shape[0] + 1, dtype=torch.int32, device=tokens2d.device)
+        cu_lens[1:] = torch.cumsum(lens, 0)
+        indices = torch.nonzero(keep.flatten(), as_tuple=False).flatten()
+        return tokens2d.flatten()[indices].contiguous(), indices, cu_lens, int(lens.max().item())
+
+    def _check_layers(self, layers):
+        layers = layers or list()
+        assert all(i < len(self.layers) for i in layers), \
+            f'Invalid layer indices {layers}. The number of layers in the model is {len(self.layers)}.'
+        return layers
+
+    def _packed(self, tokens, pad_args, kind, layers=()):
+        """Run the engine on 1-D tokens or on the packed form of 2-D tokens."""
+        if pad_args is not None:
+            assert tokens.ndim == 1, 'tokens are expected to be unpadded with shape (batch * seq_len)'
+            cu_lens, max_len = pad_args
+            indices, grid = None, None
+        else:
+            assert tokens.ndim == 2, 'tokens are expected to be padded with shape (batch, seq_len, embed_dim)'
+            grid = tuple(tokens.shape)
+            tokens, indices, cu_lens, max_len = self._unpad(tokens)
+        eng = self.engine()
+        ops._need_cuda(tokens, cu_lens)
+        assert tokens.dtype == torch.int64, 'tokens must be int64'
+        tokens = tokens.contiguous()
+        cu_lens = cu_lens.to(device=tokens.device, dtype=torch.int32).contiguous()
+        taps = {i: torch.empty(tokens.numel(), self.embed_dim, dtype=torch.bfloat16, device=tokens.device)
+                for i in layers}
+        out = eng.forward(tokens, cu_lens, int(max_len), kind, taps)
+        return out, [taps[i] for i in layers], indices, grid, (cu_lens, int(max_len))
+
+    @staticmethod
+    def _pad(x, indices, rows):
+        full = torch.zeros(rows, x.shape[-1], dtype=x.dtype, device=x.device)
+        full[indices] = x
+        return full
+
+    def forward_representation(self, tokens, pad_args=None, pad_output=False, pad_indices=None,
+                               lora_names=None, layers=None):
+        """esme/esm.py:201-266: final-LayerNorm representations [T,D] (packed) or
+        [B,S,D] (padded input / pad_output), optionally concatenated with the raw
+        outputs of the intermediate `layers` on the feature dim."""
+        if lora_names is not None:
+            raise NotImplementedError('LoRA adapters are not part of this build')
+        layers = self._check_layers(layers)
+        x, reps, indices, grid, (cu_lens, max_len) = self._packed(tokens, pad_args, L.OUT_REPRESENTATION, layers)
+        if pad_output or pad_args is None:
+            if grid is None:
+                assert pad_indices is not None, 'pad_output=True on packed tokens needs pad_indices'
+                indices, grid = pad_indices.to(x.device), (cu_lens.numel() - 1, max_len)
+            rows = grid[0] * grid[1]
+            x = self._pad(x, indices, rows).reshape(*grid, -1)
+            reps = [self._pad(r, indices, rows).reshape(*grid, -1) for r in reps]
+        if reps:
+            x = torch.concat((x, *reps), dim=-1)
+        return x
+
+    def _head_output(self, tokens, pad_args, pad_output, pad_indices, lora_names, kind):
+        if lora_names is not None:
+            raise NotImplementedError('LoRA adapters are not part of this build')
+        if pad_args is not None and not pad_output:
+            return self._packed(tokens, pad_args, kind)[0]
+        # padded output: the reference runs the LM head on every row of the padded grid,
+        # pad rows included (esme/esm.py:254-255, 281-282) -> constant lm_head(0) rows
+        z = self.forward_representation(tokens, pad_args, pad_output, pad_indices)
+        out = self.engine().lm_head(z.reshape(-1, z.shape[-1]), kind)
+        return out.reshape(*z.shape[:-1], -1)
+
+    def forward(self, tokens, pad_args=None, pad_output=False, pad_indices=None, lora_names=None):
+        """Logits: [T,V] for packed tokens + pad_args=(cu_lens, max_len); [B,S,V] for padded tokens."""
+        return self._head_output(tokens, pad_args, pad_output, pad_indices, lora_names, L.OUT_LOGITS)
+
+    def predict_log_prob(self, tokens, pad_args=None, pad_output=False, pad_indices=None, lora_names=None):
+        return self._head_output(tokens, pad_args, pad_output, pad_indices, lora_names, L.OUT_LOG_PROB)
+
+    def predict_prob(self, tokens, log=False, pad_args=None, pad_output=False, pad_indices=None, lora_names=None):
+        kind = L.OUT_LOG_PROB if log else L.OUT_PROB
+        return self._head_output(tokens, pad_args, pad_output, pad_indices, lora_names, kind)
+
+    # ---- construction / loading ----------------------------------------------
+    @classmethod
+    def create_model(cls, path, checkpointing=False):
+        """Architecture from the safetensors metadata (esme/esm.py:320-340)."""
+        meta = _read_metadata(path)
+        name = meta['name'].split('_')[0]
+        assert name == cls.__name__.lower(), \
+            f'Invalid weight for the {cls.__name__} model. ' \
+            f'You are trying to load a {name} model weights to a {cls.__name__} model.'
+        return cls(num_layers=int(meta['num_layers']), embed_dim=int(meta['embed_dim']),
+                   attention_heads=int(meta['attention_heads']), checkpointing=checkpointing)
+
+    @classmethod
+    def from_pretrained(cls, path, quantization=None, checkpointing=False, device='cpu'):
+        """esme/esm.py:343-374."""
+        assert quantization in {None, '8bit', '4bit', '8bitexperimental'}, \
+            f'load_in must be one of [None, "8bit", "4bit"] but got {quantization}'
+        if quantization is not None:
+            assert device != 'cpu', 'Quantized model cannot be loaded on cpu provide CUDA gpu device'
+            raise NotImplementedError('weight-quantized loading (bitsandbytes formats) is not part of this build yet')
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        with torch.device('meta'):
+            model = cls.create_model(path, checkpointing=checkpointing)
+        model = model.to_empty(device=device)
+        with safe_open(path, framework='pt', device=str(device)) as f:
+            keys = set(f.keys())
+            params = dict(model.named_parameters())
+            missing = sorted(set(params) - keys)
+            unexpected = sorted(keys - set(params))
+            if missing or unexpected:
+                raise RuntimeError(f'checkpoint/model mismatch: missing={missing[:5]} unexpected={unexpected[:5]}')
+            with torch.no_grad():
+                for k, p in params.items():
+                    t = f.get_tensor(k)
+                    if t.shape != p.shape:
+                        raise RuntimeError(f'shape mismatch for {k}: {tuple(t.shape)} vs {tuple(p.shape)}')
+                    p.copy_(t)
+        for m in model.modules():           # non-persistent buffers are not materialised by to_empty
+            if hasattr(m, 'inv_freq'):
+                m.inv_freq = 1.0 / (m.base ** (torch.arange(0, m.dim, 2, device=device, dtype=torch.float32) / m.dim))
+        return model.eval().requires_grad_(False)
+
+
+class ESMC(ESM2):
+    """ESM-C (reference: esme/esm.py:738-946): QK-LayerNorm, SwiGLU FFN (8/3 expansion
+    rounded up to 256), residual branches divided by sqrt(num_layers/36), 64-row
+    embedding table, no <mask>-row zeroing, bias-free final LayerNorm."""
+
+    _alphabet = Alphabet3
+    _vocab = 64
+    _embed_rows = 64
+    _zero_mask_rows = False     # esme/esm.py:876
+
+    def __init__(self, num_layers: int = 30, embed_dim: int = 960, attention_heads: int = 15,
+                 checkpointing: bool = False, dropout: float = 0., dtype=torch.bfloat16):
+        super().__init__(num_layers=num_layers, embed_dim=embed_dim, attention_heads=attention_heads,
+                         checkpointing=checkpointing, rotary_embedding=True, dropout=dropout, dtype=dtype)
+
+    def _make_layer(self, dropout, dtype):
+        return FlashTransformerLayer(self.embed_dim, 8 / 3, self.attention_heads, rotary_embedding=True,
+                                     pre_layernorm=True, bias=False, final_activation='swiglu',
+                                     residue_scaling=math.sqrt(self.num_layers / 36), dropout=dropout, dtype=dtype)
+
+    def _make_final_norm(self, dtype):
+        return nn.LayerNorm(self.embed_dim, dtype=dtype, bias=False)
+
+    def _check_layers(self, layers):
+        # the reference's check here is `i < len(layers)` (esme/esm.py:873), which rejects any useful
+        # request; this build validates against the real layer count instead.
+        return super()._check_layers(layers)

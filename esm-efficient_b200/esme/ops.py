@@ -1,0 +1,161 @@
+"""Operator-level Python wrappers over the C ABI: torch tensors in, torch tensors
+out, work enqueued on the current CUDA stream.  torch is used for device memory
+and streams only; every arithmetic kernel is in libesmk.so."""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                'esme (B200 build) runs on CUDA tensors only: the sm_100a kernels in libesmk.so are the '
+                'only backend and there is no CPU fallback. Move the model and inputs to a CUDA device.')
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor) -> Tuple[int, int]:
+    """(row count, row pitch) of a tensor whose last dim is contiguous and whose
+    leading dims form one uniformly strided row index."""
+    assert t.stride(-1) == 1, 'last dim must be contiguous'
+    if t.ndim == 1:
+        return 1, t.shape[0]
+    t2 = t if t.ndim == 2 else t.flatten(0, -2)
+    return t2.shape[0], (t2.stride(0) if t2.shape[0] > 1 else t2.shape[1])
+
+
+def batch_meta(cu_lens: torch.Tensor, T: int):
+    """-> (pos int32[T], tile_cu int32[B+1]); replaces esme/rotary.py:5-14 culen_indices."""
+    _need_cuda(cu_lens)
+    assert cu_lens.dtype == torch.int32 and cu_lens.is_contiguous()
+    B = cu_lens.numel() - 1
+    pos = torch.empty(T, dtype=torch.int32, device=cu_lens.device)
+    tile_cu = torch.empty(B + 1, dtype=torch.int32, device=cu_lens.device)
+    L.check(L.lib.esmk_batch_meta(cu_lens.data_ptr(), B, T, pos.data_ptr(), tile_cu.data_ptr(), _stream()),
+            'esmk_batch_meta')
+    return pos, tile_cu
+
+
+def rope_tables(max_len: int, head_dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    cos = torch.empty(max_len, head_dim, dtype=bf16, device=device)
+    sin = torch.empty_like(cos)
+    _need_cuda(cos)
+    L.check(L.lib.esmk_rope_tables(cos.data_ptr(), sin.data_ptr(), max_len, head_dim, _stream()), 'esmk_rope_tables')
+    return cos, sin
+
+
+def embed(tokens: torch.Tensor, table: torch.Tensor, zero_token: int = -1,
+          zero_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(tokens, table)
+    assert tokens.dtype == torch.int64 and table.dtype == bf16 and table.is_contiguous()
+    flat = tokens.reshape(-1).contiguous()
+    out = torch.empty(flat.numel(), table.shape[1], dtype=bf16, device=table.device)
+    zr = None if zero_rows is None else zero_rows.reshape(-1).to(torch.uint8).contiguous()
+    L.check(L.lib.esmk_embed(flat.data_ptr(), table.data_ptr(), out.data_ptr(), flat.numel(), table.shape[1],
+                             table.shape[0], zero_token, _ptr(zr), _stream()), 'esmk_embed')
+    return out.reshape(*tokens.shape, table.shape[1])
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    _need_cuda(x, weight)
+    assert x.dtype == bf16 and weight.dtype == bf16
+    D = x.shape[-1]
+    xc = x if x.stride(-1) == 1 else x.contiguous()
+    T, ldx = _rows(xc)
+    y = torch.empty(x.shape, dtype=bf16, device=x.device)
+    L.check(L.lib.esmk_layernorm(xc.data_ptr(), ldx, weight.data_ptr(), _ptr(bias), y.data_ptr(), D, T, D,
+                                 eps, _stream()), 'esmk_layernorm')
+    return y
+
+
+def qk_norm_rope_(q: torch.Tensor, k: torch.Tensor, H: int, head_dim: int,
+                  ln_q_weight=None, ln_k_weight=None, cos=None, sin=None, pos=None):
+    """In place on q and k ([T, H*hd] views sharing one row pitch)."""
+    _need_cuda(q, k)
+    assert q.dtype == bf16 and k.dtype == bf16 and q.shape == k.shape
+    q2, k2 = q.reshape(q.shape[0], -1), k.reshape(k.shape[0], -1)
+    assert q2.data_ptr() == q.data_ptr() and k2.data_ptr() == k.data_ptr(), 'q/k must be viewable as [T, D]'
+    T, ld = _rows(q2)
+    assert _rows(k2)[1] == ld
+    L.check(L.lib.esmk_qk_norm_rope(q2.data_ptr(), k2.data_ptr(), ld, T, H, head_dim, _ptr(ln_q_weight),
+                                    _ptr(ln_k_weight), _ptr(cos), _ptr(sin), _ptr(pos), _stream()),
+            'esmk_qk_norm_rope')
+    return q, k
+
+
+def softmax(logits: torch.Tensor, log: bool) -> torch.Tensor:
+    _need_cuda(logits)
+    assert logits.dtype == bf16
+    xc = logits.contiguous()
+    V = xc.shape[-1]
+    T = xc.numel() // V
+    out = torch.empty_like(xc)
+    L.check(L.lib.esmk_softmax(xc.data_ptr(), V, out.data_ptr(), V, T, V, int(log), _stream()), 'esmk_softmax')
+    return out
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           epilogue: int = L.EPI_BIAS, residual: Optional[torch.Tensor] = None, residue_scaling: float = 1.0,
+           rope: Optional[tuple] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epilogue(x @ weight.T + bias) through esmk_gemm (tcgen05).  `rope` =
+    (cos, sin, pos, head_dim, rope_cols) for EPI_QKV_ROPE."""
+    _need_cuda(x, weight)
+    assert x.dtype == bf16 and weight.dtype == bf16 and weight.is_contiguous()
+    K = x.shape[-1]
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    xc = x if x.stride(-1) == 1 else x.contiguous()
+    x2 = xc.reshape(-1, K)
+    M, lda = _rows(x2)
+    n_out = N // 2 if epilogue == L.EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n_out, dtype=bf16, device=x.device)
+    o2 = out.reshape(-1, n_out)
+    assert o2.data_ptr() == out.data_ptr()
+    a = L.GemmArgs()
+    a.A, a.lda, a.W, a.bias = x2.data_ptr(), lda, weight.data_ptr(), _ptr(bias)
+    a.C, a.ldc = o2.data_ptr(), _rows(o2)[1]
+    a.M, a.N, a.K, a.epilogue = M, N, K, epilogue
+    a.residue_scaling = float(residue_scaling)
+    if epilogue == L.EPI_RESIDUAL:
+        assert residual is not None and residual.dtype == bf16
+        r2 = residual.reshape(-1, N)
+        a.R, a.ldr = r2.data_ptr(), _rows(r2)[1]
+    if epilogue == L.EPI_QKV_ROPE:
+        cos, sin, pos, hd, rope_cols = rope
+        a.rope_cos, a.rope_sin, a.pos, a.head_dim, a.rope_cols = cos.data_ptr(), sin.data_ptr(), pos.data_ptr(), hd, rope_cols
+    L.check(L.lib.esmk_gemm(a, _stream()), 'esmk_gemm')
+    return out
+
+
+def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torch.Tensor, max_len: int,
+                tile_cu: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+    """q,k,v: [T,H,hd] views with a common row pitch (e.g. column blocks of the QKV
+    GEMM output) -> [T, H*hd].  Replaces flash_attn_varlen_func (esme/attention.py:115)."""
+    _need_cuda(q, k, v, cu_lens)
+    T, H, hd = q.shape
+    for t in (q, k, v):
+        assert t.dtype == bf16 and t.shape == (T, H, hd) and t.stride(2) == 1 and t.stride(1) == hd
+    ld = q.stride(0)
+    assert k.stride(0) == ld and v.stride(0) == ld
+    assert cu_lens.dtype == torch.int32
+    B = cu_lens.numel() - 1
+    if tile_cu is None:
+        _, tile_cu = batch_meta(cu_lens, T)
+    out = torch.empty(T, H * hd, dtype=bf16, device=q.device)
+    L.check(L.lib.esmk_attn_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), H * hd,
+                                   cu_lens.data_ptr(), tile_cu.data_ptr(), B, T, H, hd, int(max_len), impl,
+                                   _stream()), 'esmk_attn_varlen')
+    return out
