@@ -41,6 +41,56 @@ constexpr int P_BYTES = TILE * TILE * 2;   // 32 KB (two 128x64 swizzle atoms)
 constexpr int AT_SMEM = Q_BYTES * 3 + P_BYTES + 1024 + 128;
 constexpr int AT_TMEM_COLS = 256;    // S: [0,128)  O: [128,192)
 
+// One 128-key block of the online softmax for one query row (= one thread):
+// pass 1 reads S from TMEM for the row maximum, pass 2 re-reads it, forms P = exp2(S*c - m),
+// rounds to bf16 and writes the row into shared memory in the UMMA K-major SWIZZLE_128B layout.
+template <bool MASK>
+__device__ __forceinline__ void softmax_block(uint32_t t_row, uint8_t* prow, int rsw, int kv_valid, float scale_log2,
+                                              float& m_run, float& l_run, float& alpha) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t s[32];
+    tmem_ld32(t_row + c * 32, s);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float x = __uint_as_float(s[i]);
+      mx = (!MASK || c * 32 + i < kv_valid) ? fmaxf(mx, x) : mx;
+    }
+  }
+  const float m_new = fmaxf(m_run, mx * scale_log2);
+  alpha = fast_exp2(m_run - m_new);  // m_run = -inf on the first block -> 0
+  float rowsum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t s[32];
+    tmem_ld32(t_row + c * 32, s);
+    tmem_wait_ld();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -m_new));
+      float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_new));
+      if (MASK) {
+        p0 = (c * 32 + i < kv_valid) ? p0 : 0.f;
+        p1 = (c * 32 + i + 1 < kv_valid) ? p1 : 0.f;
+      }
+      rowsum += p0 + p1;
+      pk[i >> 1] = pack_bf16(p0, p1);
+    }
+    // keys [c*32, c*32+32) -> atom (c>>1), 16-byte chunks ((c&1)*4 .. +3) of this row, XOR-swizzled by row&7
+    uint8_t* atom = prow + (c >> 1) * (TILE * 128);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int chunk = ((c & 1) * 4 + q) ^ rsw;
+      *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+  l_run = fmaf(l_run, alpha, rowsum);
+  m_run = m_new;
+}
+
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
@@ -113,10 +163,10 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t ph = j & 1;
         const int krow = seq_start + j * TILE;
-        mbar_wait(k_empty, ph ^ 1);
+        mbar_wait_backoff(k_empty, ph ^ 1);
         mbar_arrive_expect_tx(k_full, Q_BYTES);
         tma_load_2d(sK, &tmK, k_full, col, krow);
-        mbar_wait(v_empty, ph ^ 1);
+        mbar_wait_backoff(v_empty, ph ^ 1);
         mbar_arrive_expect_tx(v_full, Q_BYTES);
         tma_load_2d(sV, &tmV, v_full, col, krow);
       }
@@ -141,8 +191,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       umma_commit(k_empty);
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t ph = j & 1;
-        mbar_wait(p_full, ph);
-        mbar_wait(v_full, ph);
+        mbar_wait_backoff(p_full, ph);
+        mbar_wait_backoff(v_full, ph);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < TILE / 16; ++k) {
@@ -153,7 +203,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         umma_commit(o_full);
         umma_commit(v_empty);
         if (j + 1 < n_kv) {
-          mbar_wait(k_full, ph ^ 1);
+          mbar_wait_backoff(k_full, ph ^ 1);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
@@ -176,52 +226,15 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t ph = j & 1;
-      const int kv_valid = L - j * TILE;  // keys [0, kv_valid) of this block exist
+      const int kv_valid = L - j * TILE;  // keys [0, kv_valid) of this block exist (< TILE only in the last block)
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // ---- pass 1: row maximum ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, s);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(s[i]));
-      }
-      const float m_new = fmaxf(m_run, mx * scale_log2);
-      const float alpha = fast_exp2(m_run - m_new);  // m_run = -inf on the first block -> 0
-      // ---- pass 2: P = exp2(S*c - m), bf16, to shared memory in UMMA K-major SW128 layout ----
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, s);
-        tmem_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kv_valid) ? fast_exp2(__uint_as_float(s[i]) * scale_log2 - m_new) : 0.f;
-          float p1 = (c * 32 + i + 1 < kv_valid) ? fast_exp2(__uint_as_float(s[i + 1]) * scale_log2 - m_new) : 0.f;
-          rowsum += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
-        }
-        // keys [c*32, c*32+32) -> atom (c>>1), 16-byte chunks ((c&1)*4 .. +3) of this row, XOR-swizzled by row&7
-        uint8_t* atom = prow + (c >> 1) * (TILE * 128);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ rsw;
-          *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
+      float alpha;
+      if (kv_valid >= TILE) softmax_block<false>(tmem_S + lane_off, prow, rsw, TILE, scale_log2, m_run, l_run, alpha);
+      else softmax_block<true>(tmem_S + lane_off, prow, rsw, kv_valid, scale_log2, m_run, l_run, alpha);
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();         // our tcgen05.ld of S are complete before the MMA warp overwrites S
       mbar_arrive(p_full);
-#pragma unroll
-      for (int i = 0; i < HD64; ++i) acc[i] *= alpha;
       mbar_wait(o_full, ph);
       tc_fence_after();
       {
@@ -230,7 +243,10 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tmem_ld32(tmem_O + lane_off + 32, o1);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { acc[i] += __uint_as_float(o0[i]); acc[32 + i] += __uint_as_float(o1[i]); }
+        for (int i = 0; i < 32; ++i) {
+          acc[i] = fmaf(acc[i], alpha, __uint_as_float(o0[i]));
+          acc[32 + i] = fmaf(acc[32 + i], alpha, __uint_as_float(o1[i]));
+        }
       }
     }
     if (q0 + r < L) {

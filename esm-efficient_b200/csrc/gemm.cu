@@ -2,7 +2,8 @@
 //
 //   warp 0      : TMA producer (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, 4-stage ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, fp32 accum in TMEM)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores);
+//                 two warps per TMEM lane quadrant, each owning one 128-column half of the tile
 //
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  Tiles are walked n-fastest so the CTAs
@@ -20,7 +21,8 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE = BN * BK * 2;  // 32 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quadrant, each owning 128 of the 256 columns
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct EpiParams {
@@ -34,23 +36,68 @@ struct EpiParams {
   const __nv_bfloat16* sinb;
   const int32_t* pos;
   int rope_cols;
-  int vec_ok;  // 16-byte stores allowed (N, ldc, ldr multiples of 8)
+  int vec_ok;  // 16-byte accesses allowed on C / R / bias (alignment and N % 8 == 0)
 };
 
-// ---- epilogue math on one 64-column group held in registers -----------------
+// exact-erf GELU, x * 0.5 * erfc(-x / sqrt 2), with erfc(a) = t * 2^(P(t) - a^2 log2 e), t = 1 / (1 + a / 2)
+// (degree-7 fit of log2(erfcx(a) / t), |relative error| < 1.5e-5 on |x| <= 8.5 in fp32, absolute < 7e-7:
+// two orders of magnitude below the bf16 rounding that follows).  17 instructions, 2 of them MUFU.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.84932180028801904f;      // |x| / sqrt(2) * sqrt(log2 e)
+  const float t = __frcp_rn(fmaf(0.41627730557884884f, z, 1.0f));  // 1 / (1 + 0.5 * |x| / sqrt 2)
+  float p = -0.23512209f;
+  p = fmaf(p, t, 0.92447854f);
+  p = fmaf(p, t, -1.14719246f);
+  p = fmaf(p, t, 0.20778944f);
+  p = fmaf(p, t, 0.11469207f);
+  p = fmaf(p, t, 0.51092552f);
+  p = fmaf(p, t, 1.45086944f);
+  p = fmaf(p, t, -1.82644122f);
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(fmaf(-z, z, p)));
+  h *= t;                                                // erfc(|x| / sqrt 2)
+  const float cdf2 = x < 0.f ? h : 2.0f - h;             // 2 * Phi(x)
+  return (0.5f * x) * cdf2;
+}
+
+// round two floats to bf16 and back (one cvt.rn.bf16x2 + two unpacks)
+__device__ __forceinline__ void bfr2(float& a, float& b) {
+  const uint32_t u = pack_bf16(a, b);
+  a = bf16_lo(u);
+  b = bf16_hi(u);
+}
+
+__device__ __forceinline__ void unpack_u4(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// ---- RoPE on one 64-column group (64 / HD whole heads) held in registers ----
+// cos/sin rows of this token are L1-resident (every head of every tile of the row-block reuses them),
+// so they are re-read 8 values at a time instead of being cached in 32 registers.
 template <int HD>
-__device__ __forceinline__ void rope64(float (&v)[64], const uint32_t (&cs)[HD / 2]) {
-  // cs[i] packs (cos[i], sin[i]) as bf16 pairs for i in [0, HD/2)
+__device__ __forceinline__ void rope64(float (&v)[64], const __nv_bfloat16* __restrict__ cos_row,
+                                       const __nv_bfloat16* __restrict__ sin_row) {
 #pragma unroll
-  for (int h = 0; h < 64 / HD; ++h) {
+  for (int i0 = 0; i0 < HD / 2; i0 += 8) {
+    float c[8], s[8];
+    unpack_u4(__ldg(reinterpret_cast<const uint4*>(cos_row + i0)), c);
+    unpack_u4(__ldg(reinterpret_cast<const uint4*>(sin_row + i0)), s);
 #pragma unroll
-    for (int i = 0; i < HD / 2; ++i) {
-      const float c = bf16_lo(cs[i]), s = bf16_hi(cs[i]);
-      const float a = v[h * HD + i], b = v[h * HD + i + HD / 2];
-      v[h * HD + i] = bfr(bfr(a * c) + bfr(-b * s));
-      v[h * HD + i + HD / 2] = bfr(bfr(b * c) + bfr(a * s));
+    for (int h = 0; h < 64 / HD; ++h) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = i0 + q;
+        const float a = v[h * HD + i], b = v[h * HD + i + HD / 2];
+        v[h * HD + i] = bfr(bfr(a * c[q]) + bfr(-b * s[q]));
+        v[h * HD + i + HD / 2] = bfr(bfr(b * c[q]) + bfr(a * s[q]));
+      }
     }
   }
+}
+
+__device__ __forceinline__ uint4 pack_u4(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
 template <int EPI, int HD>
@@ -84,7 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[a], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -106,7 +153,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = (tile / n_blocks) * BM;
         const int n0 = (tile % n_blocks) * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_backoff(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
           tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], kb * BK, m0);
           tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], kb * BK, n0);
@@ -124,11 +171,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[as], aphase ^ 1);
+        mbar_wait_backoff(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait_backoff(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE), 16, 1024, 2);
           const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * B_STAGE), 16, 1024, 2);
@@ -145,39 +192,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;    // which 128-column half of the tile this warp owns
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_blocks) * BM;
-      const int n0 = (tile % n_blocks) * BN;
+      const int n0 = (tile % n_blocks) * BN + half * 128;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
 
-      // per-row rotary constants, shared by every head in this tile
-      uint32_t cs[(EPI == ESMK_EPI_QKV_ROPE) ? HD / 2 : 1];
+      // this token's rows of the cos / sin tables (same for every head)
+      const __nv_bfloat16* cos_row = nullptr;
+      const __nv_bfloat16* sin_row = nullptr;
       if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
-        if (n0 < ep.rope_cols) {
-          const int p = row_ok ? ep.pos[row] : 0;
-          const uint32_t* c32 = reinterpret_cast<const uint32_t*>(ep.cosb + (size_t)p * HD);
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(ep.sinb + (size_t)p * HD);
-#pragma unroll
-          for (int i = 0; i < HD / 4; ++i) {
-            const uint32_t c2 = __ldg(c32 + i), s2 = __ldg(s32 + i);  // two consecutive bf16 each
-            cs[2 * i] = (c2 & 0xffffu) | (s2 << 16);
-            cs[2 * i + 1] = (c2 >> 16) | (s2 & 0xffff0000u);
-          }
-        }
+        const int p = row_ok ? ep.pos[row] : 0;
+        cos_row = ep.cosb + (size_t)p * HD;
+        sin_row = ep.sinb + (size_t)p * HD;
       }
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * 128;
 
 #pragma unroll 1
-      for (int g = 0; g < BN / 64; ++g) {
+      for (int g = 0; g < 2; ++g) {
         const int col0 = n0 + g * 64;
+        const bool full_group = ep.vec_ok && (col0 + 64 <= N);
+        // issue the independent global loads first so their latency overlaps the TMEM read
+        uint4 rq[(EPI == ESMK_EPI_RESIDUAL) ? 8 : 1];
+        if (full_group) {
+          if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+            if (row_ok) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(ep.R + (size_t)row * ep.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rq[j] = r4[j];
+            }
+          }
+        }
         float v[64];
         {
           uint32_t r0[32], r1[32];
@@ -187,7 +240,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
         }
-        if (g == BN / 64 - 1) {
+        if (g == 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -195,30 +248,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (col0 >= N) continue;
 
-        // ---- bias, first rounding point: bf(A W^T + b) ----
+        // ---- bias: bf(A W^T + b) is the first rounding point of every epilogue ----
         if (ep.bias != nullptr) {
+          if (full_group) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(ep.bias + col0);   // L1-resident, branch-free
 #pragma unroll
-          for (int j = 0; j < 64; j += 2) {
-            const int c = col0 + j;
-            float b0 = 0.f, b1 = 0.f;
-            if (c + 1 < N) {
-              const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t*>(ep.bias + c) );
-              b0 = bf16_lo(b2); b1 = bf16_hi(b2);
-            } else if (c < N) {
-              b0 = __bfloat162float(ep.bias[c]);
+            for (int j = 0; j < 8; ++j) {
+              float b[8];
+              unpack_u4(__ldg(b4 + j), b);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[8 * j + q] += b[q];
             }
-            v[j] += b0; v[j + 1] += b1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < N) v[j] += __bfloat162float(ep.bias[col0 + j]);
           }
         }
+        if constexpr (EPI != ESMK_EPI_BIAS) {   // (plain bias: the store's rounding is that rounding point)
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = bfr(v[j]);
+          for (int j = 0; j < 64; j += 2) bfr2(v[j], v[j + 1]);
+        }
 
         if constexpr (EPI == ESMK_EPI_BIAS_GELU) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 64; ++j) v[j] = gelu_fast(v[j]);
         }
         if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
-          if (col0 < ep.rope_cols) rope64<HD>(v, cs);
+          if (col0 < ep.rope_cols) rope64<HD>(v, cos_row, sin_row);
         }
 
         if constexpr (EPI == ESMK_EPI_SWIGLU) {
@@ -227,7 +284,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float a = v[j];
-            const float sl = bfr(a / (1.0f + expf(-a)));
+            const float sl = bfr(__fdividef(a, 1.0f + __expf(-a)));
             o[j] = sl * v[32 + j];
           }
           if (row_ok) {
@@ -236,12 +293,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + oc0;
             if (ep.vec_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (oc0 + j < No)
-                  *reinterpret_cast<uint4*>(dst + j) =
-                      make_uint4(pack_bf16(o[j], o[j + 1]), pack_bf16(o[j + 2], o[j + 3]),
-                                 pack_bf16(o[j + 4], o[j + 5]), pack_bf16(o[j + 6], o[j + 7]));
-              }
+              for (int j = 0; j < 32; j += 8)
+                if (oc0 + j < No) *reinterpret_cast<uint4*>(dst + j) = pack_u4(o + j);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -253,39 +306,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
         if (!row_ok) continue;
         __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + col0;
-        if constexpr (EPI == ESMK_EPI_RESIDUAL) {
-          const __nv_bfloat16* rsd = ep.R + (size_t)row * ep.ldr + col0;
-          if (ep.vec_ok) {
+        if (full_group) {
+          if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+            const float inv_is_one = ep.scale == 1.0f;
 #pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              if (col0 + j < N) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rsd + j);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            for (int j = 0; j < 8; ++j) {
+              float r[8];
+              unpack_u4(rq[j], r);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  v[j + 2 * q] = bf16_lo(w[q]) + bfr(v[j + 2 * q] / ep.scale);
-                  v[j + 2 * q + 1] = bf16_hi(w[q]) + bfr(v[j + 2 * q + 1] / ep.scale);
-                }
+              for (int q = 0; q < 8; ++q) {
+                const float y = inv_is_one ? v[8 * j + q] : bfr(v[8 * j + q] / ep.scale);
+                v[8 * j + q] = r[q] + y;
               }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (col0 + j < N) v[j] = __bfloat162float(rsd[j]) + bfr(v[j] / ep.scale);
           }
-        }
-        if (ep.vec_ok) {
 #pragma unroll
-          for (int j = 0; j < 64; j += 8) {
-            if (col0 + j < N)
-              *reinterpret_cast<uint4*>(dst + j) =
-                  make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                             pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-          }
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = pack_u4(v + 8 * j);
         } else {
+          // ragged right edge (or unaligned C): element-wise, compile-time indices keep v[] in registers
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (col0 + j < N) dst[j] = __float2bfloat16_rn(v[j]);
+          for (int j = 0; j < 64; ++j) {
+            if (col0 + j < N) {
+              float y = v[j];
+              if constexpr (EPI == ESMK_EPI_RESIDUAL)
+                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(y / ep.scale);
+              dst[j] = __float2bfloat16_rn(y);
+            }
+          }
         }
       }
     }
@@ -338,7 +385,7 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   ep.rope_cols = a.rope_cols;
   const int n_out = a.epilogue == ESMK_EPI_SWIGLU ? a.N / 2 : a.N;
   ep.vec_ok = (n_out % 8 == 0) && (a.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
-  if (a.bias != nullptr) ESMK_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 3) == 0, "bias must be 4-byte aligned");
+  if (a.bias != nullptr) ep.vec_ok = ep.vec_ok && ((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   switch (a.epilogue) {
     case ESMK_EPI_BIAS:
       return launch<ESMK_EPI_BIAS, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);

@@ -1,0 +1,91 @@
+"""Sequence-sharded multi-GPU forward (one process per GPU, torch.distributed).
+
+The reference has no inference-time multi-GPU path; sequences are
+independent (attention never crosses cu_lens boundaries), so a packed batch is
+split by whole sequences, every rank runs the single-GPU forward on its share
+with replicated weights, and ONE collective -- an all-gather of the per-rank
+logits -- restores the original token order on every rank.  No collective is
+needed inside the forward.
+"""
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def sequence_cost(length: int, embed_dim: int, ffn_factor: float = 24.0) -> float:
+    """FLOP model per sequence: L * (8 + ffn_factor) * D^2 linear work + 4 * D * L^2 attention
+    (per layer; the layer count is a common factor).  ffn_factor = 16 (ESM2) .. 6F/D (ESMC)."""
+    return length * ffn_factor * embed_dim * embed_dim + 4.0 * embed_dim * length * length
+
+
+def partition_sequences(lengths: Sequence[int], world_size: int, embed_dim: int = 1280) -> List[List[int]]:
+    """Longest-processing-time greedy: sequences sorted by cost, each given to the least
+    loaded rank.  Returns, per rank, the sorted list of sequence indices it owns."""
+    order = sorted(range(len(lengths)), key=lambda i: -sequence_cost(lengths[i], embed_dim))
+    load = [0.0] * world_size
+    owned: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        owned[r].append(i)
+        load[r] += sequence_cost(lengths[i], embed_dim)
+    return [sorted(o) for o in owned]
+
+
+def imbalance(lengths: Sequence[int], owned: List[List[int]], embed_dim: int = 1280) -> float:
+    """max / mean of the per-rank modelled cost."""
+    loads = [sum(sequence_cost(lengths[i], embed_dim) for i in o) for o in owned]
+    mean = sum(loads) / len(loads)
+    return max(loads) / mean if mean > 0 else 1.0
+
+
+def take_sequences(tokens: torch.Tensor, cu_lens: torch.Tensor, idx: Sequence[int]):
+    """Packed sub-batch made of sequences `idx`: (tokens, cu_lens int32, max_len, token_index)."""
+    cu = cu_lens.tolist()
+    if len(idx) == 0:
+        e = torch.empty(0, dtype=torch.int64)
+        return tokens[:0], torch.zeros(1, dtype=torch.int32), 0, e
+    spans = [torch.arange(cu[i], cu[i + 1], dtype=torch.int64) for i in idx]
+    token_index = torch.cat(spans)
+    lens = torch.tensor([cu[i + 1] - cu[i] for i in idx], dtype=torch.int32)
+    sub_cu = torch.zeros(len(idx) + 1, dtype=torch.int32)
+    sub_cu[1:] = torch.cumsum(lens, 0)
+    return tokens[token_index], sub_cu, int(lens.max()), token_index
+
+
+def sharded_forward(fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor], tokens: torch.Tensor,
+                    cu_lens: torch.Tensor, width: int, embed_dim: int = 1280, group=None,
+                    device=None, dtype=torch.bfloat16) -> torch.Tensor:
+    """Run `fn(tokens_r, cu_lens_r, max_len_r) -> [T_r, width]` on this rank's share of
+    the batch (host tensors in, device tensors to fn) and all-gather the results into
+    the original packed order: returns [T, width] on every rank.
+
+    tokens / cu_lens are the FULL batch as host tensors, identical on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lengths = (cu_lens[1:] - cu_lens[:-1]).tolist()
+    owned = partition_sequences(lengths, world, embed_dim)
+    shares = [take_sequences(tokens, cu_lens, o) for o in owned]
+    t_max = max(int(s[3].numel()) for s in shares)
+    tok_r, cu_r, max_len_r, _ = shares[rank]
+    local = torch.zeros(t_max, width, dtype=dtype, device=device)
+    if tok_r.numel() > 0:
+        out = fn(tok_r.to(device), cu_r.to(device), max_len_r)
+        local[:out.shape[0]] = out
+    gathered = torch.empty(world * t_max, width, dtype=dtype, device=device)
+    dist.all_gather_into_tensor(gathered, local, group=group)      # the only collective of the path
+    T = int(cu_lens[-1])
+    src = torch.cat([s[3].new_tensor(range(s[3].numel())) + r * t_max for r, s in enumerate(shares)])
+    dst = torch.cat([s[3] for s in shares])
+    result = torch.empty(T, width, dtype=dtype, device=device)
+    result[dst.to(device)] = gathered[src.to(device)]
+    return result
+
+
+def model_sharded_forward(model, tokens, cu_lens, kind: str = 'logits', group=None):
+    """Convenience wrapper for an esme model living on this rank's GPU."""
+    dev = next(model.parameters()).device
+    fns = {'logits': lambda t, c, m: model(t, (c, m)),
+           'log_prob': lambda t, c, m: model.predict_log_prob(t, (c, m))}
+    return sharded_forward(fns[kind], tokens, cu_lens, model.lm_head.final.out_features,
+                           model.embed_dim, group, dev)

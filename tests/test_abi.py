@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/esmk.h declares; argument
+errors are reported through return codes + esmk_last_error (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'esmk.h')).read()
+    return sorted(set(re.findall(r'ESMK_API[^;(]*?\b(esmk_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from esme import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 16
+    lib = C.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in include/esmk.h but not exported'
+    assert sorted(_lib.SIGNATURES) == syms          # the ctypes binding covers exactly the header
+
+
+def test_version_and_error_reporting():
+    from esme import _lib
+    assert _lib.lib.esmk_version() >= 100
+    assert _lib.lib.esmk_gemm(None, None) != 0
+    assert b'null' in _lib.lib.esmk_last_error()
+    a = _lib.GemmArgs()
+    a.M, a.N, a.K, a.lda = 4, 4, 7, 7                  # K not a multiple of 8
+    assert _lib.lib.esmk_gemm(C.byref(a), None) != 0
+    assert b'multiples of 8' in _lib.lib.esmk_last_error()
+    with pytest.raises(_lib.EsmkError):
+        _lib.check(_lib.lib.esmk_model_create(None, None, None), 'esmk_model_create')
+    assert _lib.lib.esmk_workspace_bytes(None, 10, 1, 10) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    from esme import ops
+    x = torch.zeros(4, 8, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.layernorm(x, torch.ones(8, dtype=torch.bfloat16), None)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.linear(x, torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'esm-efficient_b200')
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+                src = open(os.path.join(d, f)).read()
+                assert 'oracle' not in src, f'{f} references the oracle'

@@ -1,0 +1,160 @@
+"""Model-level parity on the GPU: the drop-in esme API (C ABI underneath) against
+  (1) the committed logits of the real reference (tests/golden, CPU bf16 path),
+  (2) the oracle in exact (fp64) mode -- the tolerance statement:
+
+      rms_rel(new, exact) <= 1.5 x rms_rel(reference, exact)      (same inputs)
+      min row cosine >= 0.9999, argmax agreement >= 98.5 %
+
+i.e. the CUDA path may be no further from the exact result than the reference's own
+bf16 noise floor (2.3e-3 RMS-relative on ESM2-8M); elementwise 1e-3
+agreement between two bf16 pipelines is below that floor and is not claimed."""
+import pytest
+import torch
+
+import esme
+from conftest import GOLDEN, err_stats, load_golden
+from esme.alphabet import Alphabet
+from oracle import esm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+CASES = [('esm2_8m.safetensors', 'esm2_8m_cfg1.npz'), ('esm2_8m.safetensors', 'esm2_8m_testfa.npz'),
+         ('esm2_tiny.safetensors', 'esm2_tiny.npz'), ('esmc_tiny.safetensors', 'esmc_tiny.npz')]
+
+
+def _load(ckpt):
+    return esme.ESM.from_pretrained(f'{GOLDEN}/{ckpt}', device=DEV)
+
+
+@pytest.mark.parametrize('ckpt,fixture', CASES)
+def test_packed_forward_matches_reference_and_oracle(ckpt, fixture):
+    g = load_golden(fixture)
+    model = _load(ckpt)
+    cfg, W = O.load_checkpoint(f'{GOLDEN}/{ckpt}')
+    tokens, cu, max_len = g['tokens'], g['cu_lens'], g['max_len']
+    got = model(tokens.to(DEV), (cu.to(DEV), max_len))
+    assert got.dtype == torch.bfloat16 and got.shape == g['logits'].shape
+    got = got.float().cpu()
+    exact = O.forward_packed(cfg, W, tokens, cu, max_len, 'fp64').float()
+    _, rms_new, cos_new, agree = err_stats(got, exact)
+    _, rms_ref, _, _ = err_stats(g['logits'], exact)
+    _, rms_pair, cos_pair, _ = err_stats(got, g['logits'])
+    assert rms_new <= 1.5 * rms_ref + 1e-4
+    assert rms_pair <= 2.5 * rms_ref + 1e-4
+    assert cos_new >= 0.9999 and cos_pair >= 0.9999 and agree >= 0.985
+    lp = model.predict_log_prob(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    assert err_stats(lp, g['log_prob'])[1] <= 2.5 * rms_ref + 1e-3
+    pr = model.predict_prob(tokens.to(DEV), pad_args=(cu.to(DEV), max_len)).float().cpu()
+    assert torch.allclose(pr.sum(-1), torch.ones(pr.shape[0]), atol=2e-2)
+    rep = model.forward_representation(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    rs = err_stats(rep, g['representation'])
+    assert rs[1] < 1.5e-2 and rs[2] > 0.998
+
+
+@pytest.mark.parametrize('ckpt,fixture', [CASES[0], CASES[2], CASES[3]])
+def test_layer_module_matches_reference_taps(ckpt, fixture):
+    """FlashTransformerLayer / RotaryEmbedding operator boundaries vs the reference's
+    layer-0 outputs (hooks in make_golden.py)."""
+    g = load_golden(fixture)
+    model = _load(ckpt)
+    tokens, cu = g['tokens'].to(DEV), g['cu_lens'].to(DEV)
+    x0 = model.embedding(tokens)
+    y0 = model.layers[0](x0, cu, g['max_len']).float().cpu()
+    _, rms, cos, _ = err_stats(y0, g['layer0.x_out'])
+    assert rms < 3e-3 and cos > 0.9999
+    sa = model.layers[0].self_attn
+    qkv, _ = sa._qkv_rot(x0, cu, g['max_len'])
+    D = model.embed_dim
+    q = qkv[:, :D].float().cpu().reshape(g['layer0.q_rot'].shape)
+    k = qkv[:, D:2 * D].float().cpu().reshape(g['layer0.k_rot'].shape)
+    assert err_stats(q.flatten(1), g['layer0.q_rot'].flatten(1))[1] < 1e-3
+    assert err_stats(k.flatten(1), g['layer0.k_rot'].flatten(1))[1] < 1e-3
+
+
+def test_rotary_module_matches_reference_bf16():
+    g = load_golden('rope.npz')
+    rot = esme.rotary.RotaryEmbedding(dim=64)
+    q, k = g['q'].bfloat16().to(DEV), g['k'].bfloat16().to(DEV)
+    qr, kr = rot(q, k, g['cu_lens'].to(DEV), g['max_len'])
+    assert torch.equal(rot._cos_cached.float().cpu(), g['cos_bf16'])
+    assert (rot._sin_cached.float().cpu() - g['sin_bf16']).abs().max() < 1e-5
+    mism = (qr.float().cpu() != g['q_rot_bf16']).float().mean().item()
+    assert mism < 1e-3 and (kr.float().cpu() - g['k_rot_bf16']).abs().max() < 1e-2
+    assert torch.equal(q.float().cpu(), g['q'].bfloat16().float())      # inputs untouched
+
+
+def test_padded_entry_matches_reference():
+    model = _load('esm2_8m.safetensors')
+    g = load_golden('esm2_8m_padded.npz')
+    got = model(g['tokens'].to(DEV))
+    assert got.shape == g['logits'].shape
+    _, rms, cos, agree = err_stats(got.float().cpu(), g['logits'])
+    assert rms < 6e-3 and cos > 0.9999 and agree > 0.98
+    pad = g['tokens'] == Alphabet.padding_idx
+    rows = got.float().cpu()[pad]
+    assert (rows - rows[0]).abs().max() == 0                            # constant lm_head(0) rows
+    lp = model.predict_log_prob(g['tokens'].to(DEV)).float().cpu()
+    assert err_stats(lp, g['log_prob'])[1] < 8e-3
+
+
+def test_packed_equals_padded_and_batch_invariance():
+    """Reference tests/test_esm.py:70-81 (packed vs padded) -- here bit-exact, plus batch
+    composition invariance (a sequence's logits do not depend on its neighbours)."""
+    model = _load('esm2_8m.safetensors')
+    g = load_golden('esm2_8m_cfg1.npz')
+    tokens, cu, max_len = g['tokens'].to(DEV), g['cu_lens'].to(DEV), g['max_len']
+    packed = model(tokens, (cu, max_len))
+    padded = model(esme.tokenize(g['seqs'], Alphabet).to(DEV))
+    assert torch.equal(padded.reshape(-1, 33), packed)
+    first = model(tokens[:66].contiguous(), (cu[:2].contiguous(), 66))
+    assert torch.equal(first, packed[:66])
+    # pad_output=True with explicit indices
+    from esme.alphabet import tokenize_unpad
+    t, idx, c, ml = tokenize_unpad(g['seqs'], Alphabet)
+    po = model(t.to(DEV), (c.to(DEV), ml), pad_output=True, pad_indices=idx.to(DEV))
+    assert torch.equal(po, padded)
+
+
+def test_intermediate_layers_and_errors():
+    model = _load('esm2_tiny.safetensors')
+    g = load_golden('esm2_tiny.npz')
+    tokens, cu, max_len = g['tokens'].to(DEV), g['cu_lens'].to(DEV), g['max_len']
+    rep = model.forward_representation(tokens, (cu, max_len), layers=[0])
+    assert rep.shape == (tokens.numel(), 2 * model.embed_dim)
+    _, rms, cos, _ = err_stats(rep[:, model.embed_dim:].float().cpu(), g['layer0.x_out'])
+    assert rms < 3e-3 and cos > 0.9999
+    with pytest.raises(AssertionError):
+        model(tokens.reshape(1, -1), (cu, max_len))                     # 2-D tokens with pad_args
+    with pytest.raises(AssertionError):
+        model(tokens)                                                   # 1-D tokens without pad_args
+
+
+def test_full_size_650m_properties():
+    """BASELINE config 2 shape (ESM2-650M, ~50k packed tokens, synthetic weights): properties
+    that do not need an oracle run at full size."""
+    cfg = O.OracleConfig('esm2', 33, 1280, 20)
+    W = O.synthetic_weights(cfg, seed=1)
+    model = esme.ESM2(33, 1280, 20)
+    model.load_state_dict(W, strict=True)
+    model = model.to(DEV).eval()
+    lens = O.synthetic_lengths(50000, seed=2)
+    tokens, cu, max_len = O.synthetic_batch(lens, seed=3)
+    logp = model.predict_log_prob(tokens.to(DEV), (cu.to(DEV), max_len))
+    assert logp.shape == (tokens.numel(), 33) and torch.isfinite(logp.float()).all()
+    assert torch.allclose(logp.float().exp().sum(-1), torch.ones(tokens.numel(), device=DEV), atol=3e-2)
+    logits = model(tokens.to(DEV), (cu.to(DEV), max_len))
+    assert torch.equal(logits, model(tokens.to(DEV), (cu.to(DEV), max_len)))      # deterministic
+    # batch-composition invariance at full size: sequences 3..5 alone == inside the 50k batch
+    a, b = int(cu[3]), int(cu[6])
+    sub_cu = (cu[3:7] - cu[3]).to(DEV)
+    alone = model(tokens[a:b].to(DEV), (sub_cu, int((cu[4:7] - cu[3:6]).max())))
+    assert torch.equal(alone, logits[a:b])
+    # a 2-sequence prefix against the oracle (finishes in seconds on CPU)
+    n = int(cu[2])
+    got = logits[:n].float().cpu()
+    exact = O.forward_packed(cfg, W, tokens[:n], cu[:3], int((cu[1:3] - cu[:2]).max()), 'fp32')
+    want = O.forward_packed(cfg, W, tokens[:n], cu[:3], int((cu[1:3] - cu[:2]).max()), 'bf16')
+    _, rms_new, cos_new, agree = err_stats(got, exact)
+    _, rms_orc, _, _ = err_stats(want, exact)
+    assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new > 0.9999 and agree > 0.97
