@@ -59,6 +59,11 @@ int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* 
                      esmk_stream_t s) {
   GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_cu, B, T, H, head_dim, max_len, impl, ST(s)));
 }
+void esmk_profile_enable(int on) { esmk::profile_enable(on); }
+int esmk_profile_read(float* ms, int* launches, int n_categories) {
+  if (ms == nullptr || launches == nullptr) return esmk::fail("esmk_profile_read", "null argument");
+  GUARD(esmk::profile_read(ms, launches, n_categories));
+}
 int esmk_model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model_t** out) {
   GUARD(esmk::model_create(cfg, w, out));
 }

@@ -28,6 +28,9 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st);
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
                 const int32_t* tile_cu, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st);
 
+void profile_enable(int on);
+int profile_read(float* ms, int* launches, int n_categories);
+
 int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out);
 size_t workspace_bytes(const esmk_model* m, int T, int B, int max_len);
 int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,

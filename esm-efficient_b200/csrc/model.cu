@@ -16,6 +16,46 @@ namespace esmk {
 
 namespace {
 
+// ---------------------------------------------------------------------------
+// Optional per-kernel-family device timing (bench.py's roofline block): CUDA event
+// pairs recorded on the launching stream around each launch of esmk_forward.
+// ---------------------------------------------------------------------------
+struct Profiler {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<std::pair<int, int>> spans;   // (category, index of start event)
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+};
+Profiler g_prof;
+
+struct Span {
+  int cat;
+  cudaStream_t st;
+  bool on;
+  Span(int c, cudaStream_t s) : cat(c), st(s), on(g_prof.enabled) {
+    if (on) {
+      g_prof.spans.emplace_back(cat, (int)g_prof.used);
+      cudaEventRecord(g_prof.get(), st);
+    }
+  }
+  ~Span() {
+    if (on) cudaEventRecord(g_prof.get(), st);
+  }
+};
+#define PROF(cat, expr)       \
+  do {                        \
+    Span _span(cat, st);      \
+    ESMK_TRY(expr);           \
+  } while (0)
+
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
 struct Workspace {
@@ -76,6 +116,26 @@ int head_and_output(const esmk_model* m, const __nv_bfloat16* z, int T, __nv_bfl
 
 }  // namespace
 
+void profile_enable(int on) {
+  g_prof.enabled = on != 0;
+  g_prof.spans.clear();
+  g_prof.used = 0;
+}
+
+// Sums the elapsed time of every recorded span per category (ms) and the launch count; the caller
+// must have synchronised the stream.  Resets the recording.
+int profile_read(float* ms, int* launches, int n_categories) {
+  for (int i = 0; i < n_categories; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  for (auto& sp : g_prof.spans) {
+    float t = 0.f;
+    ESMK_CUDA(cudaEventElapsedTime(&t, g_prof.pool[sp.second], g_prof.pool[sp.second + 1]));
+    if (sp.first >= 0 && sp.first < n_categories) { ms[sp.first] += t; launches[sp.first] += 1; }
+  }
+  g_prof.spans.clear();
+  g_prof.used = 0;
+  return 0;
+}
+
 int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out) {
   ESMK_REQUIRE(cfg && w && out, "null argument");
   ESMK_REQUIRE(cfg->family == 0 || cfg->family == 1, "family must be 0 (ESM2) or 1 (ESMC)");
@@ -125,43 +185,44 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
   const float s = c.residue_scaling;
   const bool fused_rope = (c.family == 0) && (hd <= 64) && ((2 * D) % 64 == 0);
 
-  ESMK_TRY(batch_meta(cu_lens, B, T, b.pos, b.tile_cu, st));
-  ESMK_TRY(rope_tables(b.cosb, b.sinb, max_len, hd, st));
+  PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_cu, st));
+  PROF(ESMK_PROF_MISC, rope_tables(b.cosb, b.sinb, max_len, hd, st));
   // esme/esm.py:188-189: ESM2 zeroes <mask>(32) rows; ESMC (esm.py:876) does not
-  ESMK_TRY(embed(tokens, m->w.embed, b.x, T, D, c.embed_rows, c.family == 0 ? 32 : -1, zero_rows, st));
+  PROF(ESMK_PROF_MISC, embed(tokens, m->w.embed, b.x, T, D, c.embed_rows, c.family == 0 ? 32 : -1, zero_rows, st));
 
   for (int i = 0; i < c.num_layers; ++i) {
     const esmk_layer_weights& l = m->layers[i];
     // ---- attention block: x = x + out(attn(rope(qkv(LN(x))))) / s   (esme/attention.py:126-139, 253-254)
-    ESMK_TRY(layernorm(b.x, D, l.attn_norm_w, l.attn_norm_b, b.h, D, T, D, 1e-5f, st));
+    PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.attn_norm_w, l.attn_norm_b, b.h, D, T, D, 1e-5f, st));
     if (fused_rope) {
       esmk_gemm_args g{};
       g.A = b.h; g.lda = D; g.W = l.wqkv; g.bias = l.bqkv; g.C = b.qkv; g.ldc = 3 * D;
       g.M = T; g.N = 3 * D; g.K = D; g.epilogue = ESMK_EPI_QKV_ROPE;
       g.rope_cos = b.cosb; g.rope_sin = b.sinb; g.pos = b.pos; g.head_dim = hd; g.rope_cols = 2 * D;
-      ESMK_TRY(gemm(g, st));
+      PROF(ESMK_PROF_GEMM_QKV, gemm(g, st));
     } else {
-      ESMK_TRY(linear(b.h, D, l.wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
-      ESMK_TRY(qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
+      PROF(ESMK_PROF_GEMM_QKV, linear(b.h, D, l.wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
+      PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
     }
-    ESMK_TRY(attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_cu, B, T, H, hd, max_len, 0,
-                         st));
-    ESMK_TRY(linear(b.a, D, l.wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    PROF(ESMK_PROF_ATTENTION,
+         attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_cu, B, T, H, hd, max_len, 0, st));
+    PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, l.wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)
-    ESMK_TRY(layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));
+    PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));
     if (c.family == 0) {
-      ESMK_TRY(linear(b.h, D, l.w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
+      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, l.w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
     } else {
-      ESMK_TRY(linear(b.h, D, l.w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
+      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, l.w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
     }
-    ESMK_TRY(linear(b.u, F, l.w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    PROF(ESMK_PROF_GEMM_FFN_DOWN, linear(b.u, F, l.w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     if (layer_taps != nullptr && layer_taps[i] != nullptr)
       ESMK_CUDA(cudaMemcpyAsync(layer_taps[i], b.x, (size_t)T * D * 2, cudaMemcpyDeviceToDevice, st));
   }
   // esme/esm.py:252
   if (kind == ESMK_OUT_REPRESENTATION)
     return layernorm(b.x, D, m->w.final_norm_w, m->w.final_norm_b, out, D, T, D, 1e-5f, st);
-  ESMK_TRY(layernorm(b.x, D, m->w.final_norm_w, m->w.final_norm_b, b.h, D, T, D, 1e-5f, st));
+  PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, m->w.final_norm_w, m->w.final_norm_b, b.h, D, T, D, 1e-5f, st));
+  Span head_span(ESMK_PROF_HEAD, st);
   return head_and_output(m, b.h, T, b.a, b.x, kind, out, st);
 }
 

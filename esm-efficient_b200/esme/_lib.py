@@ -84,6 +84,8 @@ SIGNATURES = {
     'esmk_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'esmk_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                              c_int, c_void_p, c_void_p, c_void_p]),
+    'esmk_profile_enable': (None, [c_int]),
+    'esmk_profile_read': (c_int, [C.POINTER(c_float), C.POINTER(c_int), c_int]),
     'esmk_lm_head': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
 }
 
@@ -97,6 +99,22 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = lib.esmk_last_error()
         raise EsmkError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+
+
+PROF_CATEGORIES = ('misc', 'layernorm', 'gemm_qkv', 'rope', 'attention', 'gemm_out', 'gemm_ffn_up',
+                   'gemm_ffn_down', 'head')
+
+
+def profile_enable(on: bool):
+    lib.esmk_profile_enable(int(on))
+
+
+def profile_read() -> dict:
+    """{category: (milliseconds, launches)} since the last read; synchronise the stream first."""
+    n = len(PROF_CATEGORIES)
+    ms, cnt = (c_float * n)(), (c_int * n)()
+    check(lib.esmk_profile_read(ms, cnt, n), 'esmk_profile_read')
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(PROF_CATEGORIES)}
 
 
 def launch_count() -> int:

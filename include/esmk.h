@@ -178,6 +178,25 @@ ESMK_API int esmk_forward(esmk_model_t* m, const int64_t* tokens, const int32_t*
 ESMK_API int esmk_lm_head(esmk_model_t* m, const void* x, int T, void* workspace, size_t workspace_bytes, int output_kind,
                  void* out, esmk_stream_t stream);
 
+/* ---- per-kernel-family device timing (measurement only) ------------------------- */
+enum esmk_prof_category {
+  ESMK_PROF_MISC = 0,          /* batch metadata, rope tables, embedding gather */
+  ESMK_PROF_LAYERNORM = 1,
+  ESMK_PROF_GEMM_QKV = 2,
+  ESMK_PROF_ROPE = 3,          /* stand-alone QK-LayerNorm + RoPE kernel (ESMC) */
+  ESMK_PROF_ATTENTION = 4,
+  ESMK_PROF_GEMM_OUT = 5,
+  ESMK_PROF_GEMM_FFN_UP = 6,
+  ESMK_PROF_GEMM_FFN_DOWN = 7,
+  ESMK_PROF_HEAD = 8,          /* LM head (2 GEMMs + LayerNorm + softmax) */
+  ESMK_PROF_COUNT = 9
+};
+/* When enabled, esmk_forward brackets every launch with CUDA events on its stream.
+ * esmk_profile_read (after the caller synchronised the stream) returns the summed
+ * milliseconds and launch counts per category since the last read, and resets. */
+ESMK_API void esmk_profile_enable(int on);
+ESMK_API int esmk_profile_read(float* ms, int* launches, int n_categories);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,9 @@ def load_checkpoint(path: str) -> Tuple[OracleConfig, Dict[str, torch.Tensor]]:
 # --------------------------------------------------------------------------
 # numerics helpers
 # --------------------------------------------------------------------------
+_WEIGHT_CACHE: Dict[tuple, tuple] = {}
+
+
 class _Prec:
     def __init__(self, mode: str):
         assert mode in ('bf16', 'fp32', 'fp64')
@@ -151,7 +154,16 @@ class _Prec:
         return x
 
     def w(self, t: torch.Tensor) -> torch.Tensor:
-        return t.to(self.dt)
+        """Weights widened to the compute dtype (cached: repeated forwards, e.g. the CPU
+        baseline of bench.py, must not pay the bf16 -> fp32 conversion every call)."""
+        if t.dtype == self.dt:
+            return t
+        key = (t.data_ptr(), tuple(t.shape), self.dt)
+        hit = _WEIGHT_CACHE.get(key)
+        if hit is None or hit[0] is not t:
+            hit = (t, t.to(self.dt))
+            _WEIGHT_CACHE[key] = hit
+        return hit[1]
 
 
 def _layer_norm(x, w, b, eps=1e-5):
@@ -314,11 +326,14 @@ def log_softmax(logits: torch.Tensor, mode: str = 'bf16'):
 # --------------------------------------------------------------------------
 # synthetic checkpoints / batches -- shared by tests and bench
 # --------------------------------------------------------------------------
-def synthetic_weights(cfg: OracleConfig, seed: int = 1, qk_gain: float = 4.0) -> Dict[str, torch.Tensor]:
+def synthetic_weights(cfg: OracleConfig, seed: int = 1, qk_gain: Optional[float] = None) -> Dict[str, torch.Tensor]:
     """Seeded random-init bf16 weights with the reference's key schema
-    (SURVEY.md §3.2).  Linear ~ N(0, 0.02^2) (q,k scaled by qk_gain so the
-    softmax is not uniform), LN weight 1+N(0,0.02^2), biases N(0,0.02^2)."""
+    (SURVEY.md §3.2).  Linear ~ N(0, 0.02^2) (q,k scaled by qk_gain, default
+    sqrt(2/(D*0.02^2)) -> attention logits of std ~2: non-uniform but well
+    conditioned), LN weight 1+N(0,0.02^2), biases N(0,0.02^2)."""
     g = torch.Generator().manual_seed(seed)
+    if qk_gain is None:
+        qk_gain = math.sqrt(2.0 / (cfg.embed_dim * 0.02 ** 2))
     D, F, V = cfg.embed_dim, cfg.ffn_dim, cfg.vocab
     bias = cfg.family == 'esm2'
     W: Dict[str, torch.Tensor] = {}

@@ -147,7 +147,7 @@ def main():
         ('esmc', ESMC, (2, 192, 3), 12, [200, 70, 2, 130]),
     ]:
         cfg = O.OracleConfig(family, *dims)
-        W = O.synthetic_weights(cfg, seed=seed)
+        W = O.synthetic_weights(cfg, seed=seed, qk_gain=4.0)
         path = f'{HERE}/{family}_tiny.safetensors'
         O.save_checkpoint(path, cfg, W, tag='tiny')
         m = build(cls, path)
