@@ -1,7 +1,7 @@
 """Seeded synthetic checkpoints and packed batches for benchmarks and full-size
 tests (no network: the 650M / 3B / ESMC weights cannot be downloaded).  The
-recipes are those of SURVEY.md §8d; `tests/test_synthetic.py` checks they are
-identical to the oracle's own generators.
+recipes are those of SURVEY.md §8d; `tests/test_synthetic.py` pins them against
+the test infrastructure's own copy.
 
 The batch rule is the reference's token-budget sampler (esme/data.py:42-51):
 sequences are appended in draw order until the next one would exceed the budget.

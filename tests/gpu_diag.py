@@ -251,6 +251,86 @@ def attn64_small():
 
 
 @case
+def attn64_v1():
+    out = {}
+    for name, lens in (('one_tile', [128]), ('ragged', [300, 131, 66, 2, 129, 257, 1]), ('long', [1026, 700, 3, 513])):
+        got, want = _attn_case(lens, 3, 64, impl=2, qk_scale=1.5)
+        _cmp(f'attn64v1_{name}', got, want, out)
+    return out
+
+
+@case
+def attn64_rescale():
+    """Scores whose row maximum keeps growing by > 2^8 block after block: exercises the lazy O rescale."""
+    torch, ops, L, O = _imports()
+    out = {}
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(1)
+    p = O._Prec('bf16')
+    H, hd, Ls = 2, 64, [640, 300]
+    T, D = sum(Ls), H * hd
+    q = torch.randn(T, D, generator=g)
+    k = torch.randn(T, D, generator=g)
+    v = torch.randn(T, D, generator=g)
+    ramp = torch.cat([torch.arange(l) for l in Ls]).float() / 128.0       # later keys score much higher
+    k = k * (1.0 + 3.0 * ramp[:, None])
+    qkv = torch.cat([q * 2.0, k, v], 1).bfloat16()
+    cu = torch.tensor([0, 640, 940], dtype=torch.int32)
+    qq, kk, vv = (qkv[:, i * D:(i + 1) * D].float().reshape(T, H, hd) for i in range(3))
+    want = O.varlen_attention(qq, kk, vv, cu, p).reshape(T, D)
+    qd = qkv.to(dev)
+    a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    got = ops.attn_varlen(a, b, c, cu.to(dev), 640, impl=0)
+    _cmp('attn64_rescale', got, want, out)
+    got1 = ops.attn_varlen(a, b, c, cu.to(dev), 640, impl=1)
+    _cmp('generic_rescale', got1, want, out)
+    return out
+
+
+@case
+def perf_attn():
+    torch, ops, L, O = _imports()
+    dev = 'cuda'
+    out = {}
+    lens = O.synthetic_lengths(50000, seed=2)
+    T, H, hd = sum(lens), 20, 64
+    D = H * hd
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    cu = cu.to(dev)
+    qkv = torch.randn(T, 3 * D, device=dev).bfloat16()
+    q, k, v = (qkv[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    flops = 4.0 * D * sum(l * l for l in lens)
+    _, tile_cu = ops.batch_meta(cu, T)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for name, impl in (('v2_tmem', 0), ('v1_smem', 2)):
+        ms = timeit(lambda: ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=impl))
+        out[name] = dict(ms=ms, tflops=flops / ms / 1e9)
+    try:
+        from flash_attn import flash_attn_varlen_func
+        qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+        ms = timeit(lambda: flash_attn_varlen_func(qc, kc, vc, cu, cu, max(lens), max(lens)))
+        out['flash_attn_2.8.3_library'] = dict(ms=ms, tflops=flops / ms / 1e9)
+        a = ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=0).float()
+        b = flash_attn_varlen_func(qc, kc, vc, cu, cu, max(lens), max(lens)).reshape(T, D).float()
+        out['v2_vs_flash_attn_max_abs'] = (a - b).abs().max().item()
+    except Exception as e:                                  # library baseline is optional
+        out['flash_attn_error'] = repr(e)[:200]
+    return out
+
+
+@case
 def attn64_big():
     out = {}
     got, want = _attn_case([1026, 700, 3, 2050, 513], 20, 64, impl=0, qk_scale=2.0, seed=3)

@@ -156,5 +156,8 @@ def test_full_size_650m_properties():
     exact = O.forward_packed(cfg, W, tokens[:n], cu[:3], int((cu[1:3] - cu[:2]).max()), 'fp32')
     want = O.forward_packed(cfg, W, tokens[:n], cu[:3], int((cu[1:3] - cu[:2]).max()), 'bf16')
     _, rms_new, cos_new, agree = err_stats(got, exact)
-    _, rms_orc, _, _ = err_stats(want, exact)
-    assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new > 0.9999 and agree > 0.97
+    _, rms_orc, cos_orc, agree_orc = err_stats(want, exact)
+    # 33 layers of random weights amplify bf16 rounding noise to ~1.5 % RMS: the CUDA path must sit at
+    # the same distance from the exact result as the bf16-faithful oracle does (no worse, same inputs)
+    assert rms_new <= 1.5 * rms_orc + 1e-4
+    assert cos_new >= min(0.9999, cos_orc - 2e-4) and agree >= agree_orc - 0.02
