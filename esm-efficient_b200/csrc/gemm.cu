@@ -11,6 +11,8 @@
 //
 // Fused epilogues reproduce the reference's bf16 rounding points (SURVEY.md
 // Appendix A): see enum esmk_epilogue in include/esmk.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "esmk_internal.h"
 
@@ -23,7 +25,9 @@ constexpr int A_STAGE = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE = BN * BK * 2;  // 32 KB
 constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quadrant, each owning 128 of the 256 columns
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STAGES_PAIR = 6;         // 2-CTA mode: 16 KB A + 16 KB half-W per stage
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(STAGES_PAIR * (A_STAGE + B_STAGE / 2) == STAGES * (A_STAGE + B_STAGE), "same smem footprint");
 
 struct EpiParams {
   __nv_bfloat16* C;
@@ -99,24 +103,92 @@ __device__ __forceinline__ uint4 pack_u4(const float* f) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
-template <int EPI, int HD>
+// ---- cluster / 2-CTA helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are credited to the barrier at `bar_cluster_addr`
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs retire) on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// PAIR = false: one CTA per 128x256 tile (UMMA 128x256x16, cta_group::1), 4 smem stages of 48 KB.
+// PAIR = true : a cluster of two CTAs (one TPC) per 256x256 tile (UMMA 256x256x16, cta_group::2): each CTA
+//               stages its own 128 rows of A and HALF of the W tile (128 rows), so W crosses L2->smem once per
+//               pair and a stage is 32 KB -> 6 stages.  The leader CTA (rank 0) issues the MMAs for both; each CTA
+//               drains its own 128 accumulator rows from its own TMEM.
+template <int EPI, int HD, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
             EpiParams ep) {
+  constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
+  constexpr int BSTAGE = PAIR ? B_STAGE / 2 : B_STAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE + B_STAGE));
-  uint64_t* full = bars;                  // [STAGES]
-  uint64_t* empty = bars + STAGES;        // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES; // [2]
+  uint8_t* sB = smem + NSTAGE * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * (A_STAGE + BSTAGE));
+  uint64_t* full = bars;                  // [NSTAGE]
+  uint64_t* empty = bars + NSTAGE;        // [NSTAGE]
+  uint64_t* acc_full = bars + 2 * NSTAGE; // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blocks = (M + BM - 1) / BM;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;     // 0 = leader
+  const int group = PAIR ? (blockIdx.x >> 1) : blockIdx.x; // tile-walking unit (CTA or CTA pair)
+  const int n_groups = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
+  const int m_blocks = (M + TILE_M - 1) / TILE_M;
   const int n_blocks = (N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
   const int num_k = (K + BK - 1) / BK;
@@ -124,50 +196,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], PAIR ? 2 : 1);   // pair: leader's expect_tx arrive + the peer producer's remote arrive
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, 512);
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of W) ===============
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * BM;
-        const int n0 = (tile % n_blocks) * BN;
+      for (int tile = group; tile < num_tiles; tile += n_groups) {
+        const int m0 = (tile / n_blocks) * TILE_M + rank * BM;
+        const int n0 = (tile % n_blocks) * BN + (PAIR ? rank * (BN / 2) : 0);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait_backoff(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], A_STAGE + B_STAGE);
-          tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], kb * BK, m0);
-          tma_load_2d(sB + stage * B_STAGE, &tmB, &full[stage], kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if constexpr (PAIR) {
+            const uint32_t leader_full = mapa_u32(smem_u32(&full[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE + BSTAGE));
+            else mbar_arrive_cluster(leader_full);
+            tma_load_2d_pair(sA + stage * A_STAGE, &tmA, leader_full, kb * BK, m0);
+            tma_load_2d_pair(sB + stage * BSTAGE, &tmB, leader_full, kb * BK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], A_STAGE + BSTAGE);
+            tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], kb * BK, m0);
+            tma_load_2d(sB + stage * BSTAGE, &tmB, &full[stage], kb * BK, n0);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    // ===================== MMA issuer (pair: leader CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = group; tile < num_tiles; tile += n_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait_backoff(&acc_empty[as], aphase ^ 1);
@@ -177,16 +261,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait_backoff(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(sA + stage * A_STAGE), 16, 1024, 2);
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * B_STAGE), 16, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + stage * BSTAGE), 16, 1024, 2);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // free this smem stage (in both CTAs) once the MMAs above retire
+          if constexpr (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
+        if constexpr (PAIR) umma_commit_pair(&acc_full[as]); else umma_commit(&acc_full[as]);
       }
     }
   } else {
@@ -194,10 +280,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;    // which 128-column half of the tile this warp owns
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = group; tile < num_tiles; tile += n_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_blocks) * BM;
+      const int m0 = (tile / n_blocks) * TILE_M + rank * BM;
       const int n0 = (tile % n_blocks) * BN + half * 128;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
@@ -243,7 +329,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+            else mbar_arrive(&acc_empty[as]);
+          }
         }
         if (col0 >= N) continue;
 
@@ -338,27 +427,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int EPI, int HD>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep,
-           cudaStream_t st) {
-  auto kern = gemm_kernel<EPI, HD>;
+bool use_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ESMK_GEMM_PAIR");
+    mode = (e == nullptr || e[0] != '0') ? 1 : 0;   // default: 2-CTA (cta_group::2) kernels
+  }
+  return mode == 1;
+}
+
+template <int EPI, int HD, bool PAIR>
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep,
+                cudaStream_t st) {
+  auto kern = gemm_kernel<EPI, HD, PAIR>;
   static bool configured = false;
   if (!configured) {
     ESMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, M, N, K, ep);
+  const int tile_m = PAIR ? 2 * BM : BM;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const int pairs = sm_count() / 2;
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
+  }
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, ep));
   count_launch();
-  ESMK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -368,9 +482,10 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   ESMK_REQUIRE(a.M >= 0 && a.N >= 1 && a.K >= 1, "bad GEMM shape");
   ESMK_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0, "GEMM needs K and lda to be multiples of 8 (16-byte TMA pitch)");
   if (a.M == 0) return 0;
+  const bool pair = use_pair_mode();
   CUtensorMap tmA, tmB;
   ESMK_TRY(make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, BM, BK, 128));
-  ESMK_TRY(make_tmap_2d(&tmB, a.W, a.N, a.K, a.K, BN, BK, 128));
+  ESMK_TRY(make_tmap_2d(&tmB, a.W, a.N, a.K, a.K, pair ? BN / 2 : BN, BK, 128));
   EpiParams ep{};
   ep.C = (__nv_bfloat16*)a.C;
   ep.ldc = a.ldc;
@@ -387,23 +502,30 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   if (a.bias != nullptr) ep.vec_ok = ep.vec_ok && ((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   switch (a.epilogue) {
     case ESMK_EPI_BIAS:
-      return launch<ESMK_EPI_BIAS, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_BIAS_GELU:
-      return launch<ESMK_EPI_BIAS_GELU, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS_GELU, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS_GELU, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_RESIDUAL:
       ESMK_REQUIRE(a.R != nullptr && a.residue_scaling != 0.f, "residual epilogue needs R and a non-zero scale");
       ep.vec_ok = ep.vec_ok && (a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
-      return launch<ESMK_EPI_RESIDUAL, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_RESIDUAL, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_RESIDUAL, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_SWIGLU:
       ESMK_REQUIRE(a.N % 64 == 0, "SwiGLU epilogue needs N (= 2F) to be a multiple of 64");
       ESMK_REQUIRE(a.bias == nullptr, "SwiGLU epilogue has no bias (ESMC linears are bias-free)");
-      return launch<ESMK_EPI_SWIGLU, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_SWIGLU, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_SWIGLU, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_QKV_ROPE:
       ESMK_REQUIRE(a.rope_cos && a.rope_sin && a.pos, "QKV_ROPE epilogue needs cos/sin tables and positions");
       ESMK_REQUIRE(a.rope_cols % 64 == 0 && a.rope_cols <= a.N, "rope_cols must be a multiple of 64 and <= N");
-      if (a.head_dim == 64) return launch<ESMK_EPI_QKV_ROPE, 64>(tmA, tmB, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 32) return launch<ESMK_EPI_QKV_ROPE, 32>(tmA, tmB, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 16) return launch<ESMK_EPI_QKV_ROPE, 16>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 64) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 32) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 32, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 32, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 16) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 16, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 16, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
       return fail("esmk_gemm", "fused QKV_ROPE supports head_dim 16/32/64; use ESMK_EPI_BIAS + esmk_qk_norm_rope");
     default:
       return fail("esmk_gemm", "unknown epilogue");

@@ -288,6 +288,40 @@ def attn64_rescale():
 
 
 @case
+def attn_accuracy():
+    """v2 / v1 / generic / flash-attn (the reference's kernel) against an exact fp64 attention on the same
+    bf16 inputs: the CUDA kernels must not be further from the exact result than the reference's kernel."""
+    torch, ops, L, O = _imports()
+    dev = 'cuda'
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    H, hd, lens = 4, 64, [700, 1300, 90, 257]
+    T, D = sum(lens), H * hd
+    qkv = torch.randn(T, 3 * D, generator=g)
+    qkv[:, :2 * D] *= 1.4
+    qkv = qkv.bfloat16()
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    p64 = O._Prec('fp64')
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().reshape(T, H, hd) for i in range(3))
+    exact = O.varlen_attention(q, k, v, cu, p64).reshape(T, D)
+    qd = qkv.to(dev)
+    a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    for name, impl in (('v2_tmem', 0), ('v1_smem', 2), ('generic', 1)):
+        _cmp(name, ops.attn_varlen(a, b, c, cu.to(dev), max(lens), impl=impl), exact, out)
+    _cmp('oracle_bf16', O.varlen_attention(q.float(), k.float(), v.float(), cu, O._Prec('bf16')).reshape(T, D), exact, out)
+    _cmp('exact_rounded_to_bf16', exact.bfloat16(), exact, out)
+    try:
+        from flash_attn import flash_attn_varlen_func
+        fa = flash_attn_varlen_func(a.contiguous(), b.contiguous(), c.contiguous(), cu.to(dev), cu.to(dev),
+                                    max(lens), max(lens))
+        _cmp('flash_attn_library', fa.reshape(T, D), exact, out)
+    except Exception as e:
+        out['flash_attn_error'] = repr(e)[:200]
+    return out
+
+
+@case
 def perf_attn():
     torch, ops, L, O = _imports()
     dev = 'cuda'
