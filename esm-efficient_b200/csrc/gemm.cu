@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completion bytes are credited to the barrier at `bar_cluster_addr`
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
@@ -197,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full[s], PAIR ? 2 : 1);   // pair: leader's expect_tx arrive + the peer producer's remote arrive
+      mbar_init(&full[s], 1);   // pair: the leader arms it with the bytes of BOTH CTAs' loads
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -231,8 +231,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait_backoff(&empty[stage], phase ^ 1);
           if constexpr (PAIR) {
             const uint32_t leader_full = mapa_u32(smem_u32(&full[stage]), 0);
+            // the peer's TMA completions are credited to the leader's barrier by byte count; only the leader arrives
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE + BSTAGE));
-            else mbar_arrive_cluster(leader_full);
             tma_load_2d_pair(sA + stage * A_STAGE, &tmA, leader_full, kb * BK, m0);
             tma_load_2d_pair(sB + stage * BSTAGE, &tmB, leader_full, kb * BK, n0);
           } else {

@@ -35,7 +35,7 @@ if mode == 'model':
     print('ok', y.shape)
 else:
     M, N, K, epi = {'qkv': (50000, 3840, 1280, L.EPI_BIAS), 'gelu': (50000, 5120, 1280, L.EPI_BIAS_GELU),
-                    'down': (50000, 1280, 5120, L.EPI_BIAS)}[mode]
+                    'down': (50000, 1280, 5120, L.EPI_BIAS), 'big': (8192, 8192, 8192, L.EPI_BIAS)}[mode]
     x = torch.randn(M, K, device=dev).bfloat16()
     w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
     b = torch.randn(N, device=dev).bfloat16()
