@@ -558,6 +558,269 @@ attn64v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
+// tcgen05 kernel v3, head_dim = 64: v2's dataflow (P and O in tensor memory, lazy rescale) with TWO
+// threads per query row -- 8 softmax warps per CTA, 16 per SM -- so the exponentials (MUFU) and their
+// dependent chains are covered by four warps per scheduler instead of two.  Thread (row r, half hf)
+// owns key columns [64 hf, 64 hf + 64) of its row: one TMEM read of S per block (64 values stay in
+// registers), the row maximum is exchanged with the partner thread through shared memory, row sums stay
+// per-thread partials until the epilogue, and each half rescales / normalises 32 of the 64 O columns.
+// ---------------------------------------------------------------------------
+constexpr int A3_THREADS = 64 + 256;
+constexpr int A3_SMEM = Q_BYTES * 5 + 1024 + 128 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
+                        2 * TILE * 4 /*row-sum exchange*/;
+
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(A3_THREADS, 2)
+attn64v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
+                const int32_t* __restrict__ cu_lens, const int32_t* __restrict__ tile_cu, int B, float scale_log2) {
+  const int tq = blockIdx.x;
+  if (tq >= tile_cu[B]) return;
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (tile_cu[mid] <= tq) lo = mid; else hi = mid;
+  }
+  const int seq_start = cu_lens[lo];
+  const int L = cu_lens[lo + 1] - seq_start;
+  const int q0 = (tq - tile_cu[lo]) * TILE;
+  const int n_kv = (L + TILE - 1) / TILE;
+  const int head = blockIdx.y;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
+  uint8_t* sV = sK + 2 * Q_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Q_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* x_max = reinterpret_cast<float*>(bars + 16);   // [2 parity][2 half][TILE]
+  float* x_sum = x_max + 4 * TILE;                       // [2 half][TILE]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 256);
+    mbar_init(p_full, 256);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_P = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + 192;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const int col = head * HD64;
+      mbar_arrive_expect_tx(bar_q, Q_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, col, seq_start + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int krow = seq_start + j * TILE;
+        mbar_wait_backoff(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
+        tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
+        mbar_wait_backoff(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
+        tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major from smem
+      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
+      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, 1024, 2);
+      mbar_wait_backoff(bar_q, 0);
+      mbar_wait_backoff(&k_full[0], 0);
+      tc_fence_after();
+      {
+        const uint64_t kdesc = make_smem_desc(smem_u32(sK), 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+      }
+      umma_commit(s_full);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        if (j + 1 < n_kv) {
+          const int st1 = (j + 1) & 1;
+          const uint32_t ph1 = ((j + 1) >> 1) & 1;
+          mbar_wait_backoff(s_free, j & 1);           // S_j has been copied to registers
+          mbar_wait_backoff(&k_full[st1], ph1);
+          tc_fence_after();
+          const uint64_t kdesc = make_smem_desc(smem_u32(sK + st1 * Q_BYTES), 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full);
+          umma_commit(&k_empty[st1]);
+        }
+        mbar_wait_backoff(p_full, j & 1);
+        mbar_wait_backoff(&v_full[st], ph);
+        tc_fence_after();
+        const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < TILE / 16; ++k)   // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
+          umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
+        umma_commit(o_done);
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ===================== softmax warps: two threads per query row =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant
+    const int hf = (warp - 2) >> 2;            // which 64-key half of each block / 32-column half of O
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_S + lane_off + hf * 64;
+    const uint32_t tP = tmem_P + lane_off + hf * 32;
+    const uint32_t tO = tmem_O + lane_off + hf * 32;
+    float m_ref = -INFINITY, l_part = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv_valid = L - j * TILE - hf * 64;   // valid keys among this thread's 64 columns
+      const bool masked = kv_valid < 64;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sa[32], sb[32];
+      tmem_ld32(tS, sa);
+      tmem_ld32(tS + 32, sb);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);                            // both halves arrived -> S may be overwritten
+      // ---- row maximum of this half, exchanged with the partner thread ----
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      if (masked) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m0 = fmaxf(m0, i < kv_valid ? __uint_as_float(sa[i]) : -INFINITY);
+          m1 = fmaxf(m1, i + 1 < kv_valid ? __uint_as_float(sa[i + 1]) : -INFINITY);
+          m2 = fmaxf(m2, 32 + i < kv_valid ? __uint_as_float(sb[i]) : -INFINITY);
+          m3 = fmaxf(m3, 33 + i < kv_valid ? __uint_as_float(sb[i + 1]) : -INFINITY);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m0 = fmaxf(m0, __uint_as_float(sa[i]));
+          m1 = fmaxf(m1, __uint_as_float(sa[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sb[i]));
+          m3 = fmaxf(m3, __uint_as_float(sb[i + 1]));
+        }
+      }
+      float* xm = x_max + (j & 1) * 2 * TILE;
+      const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      xm[hf * TILE + r] = mine;
+      softmax_bar();
+      const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
+      bool o_waited = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        const bool grow = mx > m_ref + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {          // same rows, same decision in the partner warp
+          const float m_new = grow ? mx : m_ref;
+          const float f = fast_exp2(m_ref - m_new);
+          mbar_wait(o_done, (j - 1) & 1);
+          o_waited = true;
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[16];
+            tmem_ld16(tO + h * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st16(tO + h * 16, o);
+          }
+          tmem_wait_st();
+          l_part *= f;
+          m_ref = m_new;
+        }
+      }
+      // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM (two 16-column stores keep the register peak low) ----
+      if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      {
+        uint32_t pk[16];
+        l_part += masked ? exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk)
+                         : exp_pack32<false>(sa, 0, kv_valid, scale_log2, m_ref, pk);
+        tmem_st16(tP, pk);
+      }
+      {
+        uint32_t pk[16];
+        l_part += masked ? exp_pack32<true>(sb, 32, kv_valid, scale_log2, m_ref, pk)
+                         : exp_pack32<false>(sb, 32, kv_valid, scale_log2, m_ref, pk);
+        tmem_st16(tP + 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: total row sum, then O / l for this thread's 32 columns ----
+    x_sum[hf * TILE + r] = l_part;
+    softmax_bar();
+    const float inv = 1.0f / (l_part + x_sum[(hf ^ 1) * TILE + r]);
+    mbar_wait(o_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld32(tO, o);
+    tmem_wait_ld();
+    if (q0 + r < L) {
+      __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + head * HD64 + hf * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8)
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(
+            pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+            pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+            pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+            pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // CUDA-core kernel: one warp per (query token, head); lanes = keys for the
 // scores, lanes = output features for P.V.
 // ---------------------------------------------------------------------------
@@ -639,7 +902,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
   ESMK_REQUIRE(hd % 8 == 0 && hd <= 128, "head_dim must be a multiple of 8 and <= 128");
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
-  if (hd == 64 && (impl == 0 || impl == 2)) {
+  if (hd == 64 && (impl == 0 || impl == 2 || impl == 3)) {
     ESMK_REQUIRE(tile_cu != nullptr, "tile_cu (esmk_batch_meta) required");
     CUtensorMap tq, tk, tv;
     ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
@@ -649,10 +912,14 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     if (!configured) {
       ESMK_CUDA(cudaFuncSetAttribute(attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
       ESMK_CUDA(cudaFuncSetAttribute(attn64v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+      ESMK_CUDA(cudaFuncSetAttribute(attn64v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM));
       configured = true;
     }
     dim3 grid((T + TILE - 1) / TILE + B, H);
     if (impl == 0)
+      attn64v3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
+                                                          scale_log2);
+    else if (impl == 3)
       attn64v2_kernel<<<grid, AT_THREADS, A2_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
                                                           scale_log2);
     else

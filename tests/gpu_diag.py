@@ -307,7 +307,7 @@ def attn_accuracy():
     exact = O.varlen_attention(q, k, v, cu, p64).reshape(T, D)
     qd = qkv.to(dev)
     a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
-    for name, impl in (('v2_tmem', 0), ('v1_smem', 2), ('generic', 1)):
+    for name, impl in (('v3_tmem_2thr', 0), ('v2_tmem', 3), ('v1_smem', 2), ('generic', 1)):
         _cmp(name, ops.attn_varlen(a, b, c, cu.to(dev), max(lens), impl=impl), exact, out)
     _cmp('oracle_bf16', O.varlen_attention(q.float(), k.float(), v.float(), cu, O._Prec('bf16')).reshape(T, D), exact, out)
     _cmp('exact_rounded_to_bf16', exact.bfloat16(), exact, out)
@@ -348,7 +348,7 @@ def perf_attn():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
-    for name, impl in (('v2_tmem', 0), ('v1_smem', 2)):
+    for name, impl in (('v3_tmem_2thr', 0), ('v2_tmem', 3), ('v1_smem', 2)):
         ms = timeit(lambda: ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=impl))
         out[name] = dict(ms=ms, tflops=flops / ms / 1e9)
     try:
@@ -358,7 +358,7 @@ def perf_attn():
         out['flash_attn_2.8.3_library'] = dict(ms=ms, tflops=flops / ms / 1e9)
         a = ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=0).float()
         b = flash_attn_varlen_func(qc, kc, vc, cu, cu, max(lens), max(lens)).reshape(T, D).float()
-        out['v2_vs_flash_attn_max_abs'] = (a - b).abs().max().item()
+        out['v3_vs_flash_attn_max_abs'] = (a - b).abs().max().item()
     except Exception as e:                                  # library baseline is optional
         out['flash_attn_error'] = repr(e)[:200]
     return out
