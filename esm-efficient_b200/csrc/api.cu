@@ -29,8 +29,9 @@ const char* esmk_last_error(void) { return esmk::last_error().c_str(); }
 int esmk_version(void) { return 100; }
 uint64_t esmk_launch_count(void) { return esmk::launch_count(); }
 
-int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, esmk_stream_t s) {
-  GUARD(esmk::batch_meta(cu_lens, B, T, pos, tile_cu, ST(s)));
+int esmk_tile_capacity(int T, int B) { return (T < 0 || B < 0) ? 0 : esmk::tile_capacity(T, B); }
+int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_info, esmk_stream_t s) {
+  GUARD(esmk::batch_meta(cu_lens, B, T, pos, tile_info, ST(s)));
 }
 int esmk_rope_tables(void* cosb, void* sinb, int max_len, int head_dim, esmk_stream_t s) {
   GUARD(esmk::rope_tables(cosb, sinb, max_len, head_dim, ST(s)));
@@ -55,9 +56,9 @@ int esmk_gemm(const esmk_gemm_args* a, esmk_stream_t s) {
   GUARD(esmk::gemm(*a, ST(s)));
 }
 int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
-                     const int32_t* tile_cu, int B, int T, int H, int head_dim, int max_len, int impl,
+                     const int32_t* tile_info, int B, int T, int H, int head_dim, int max_len, int impl,
                      esmk_stream_t s) {
-  GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_cu, B, T, H, head_dim, max_len, impl, ST(s)));
+  GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_info, B, T, H, head_dim, max_len, impl, ST(s)));
 }
 void esmk_profile_enable(int on) { esmk::profile_enable(on); }
 int esmk_profile_read(float* ms, int* launches, int n_categories) {

@@ -1,22 +1,26 @@
 // Variable-length (cu_seqlens-packed) multi-head attention, non-causal.
 //
-// attn64_kernel (head_dim 64): one CTA per (128-query tile, head).
-//   warp 0     : TMA producer  (Q once; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B)
-//   warp 1     : tcgen05.mma issuer:  S = Q K_j^T  (UMMA 128x128x16, K-major operands)
-//                                      O_j = P_j V_j (UMMA 128x64x16, P K-major from smem, V MN-major)
-//   warps 2..5 : online softmax, one query row per thread: S is read from TMEM
-//                (tcgen05.ld), P is rounded to bf16 and written to shared memory in
-//                the 128-byte-swizzled UMMA layout, O_j is read back from TMEM and
-//                accumulated in registers with the running-max correction.
-//   Two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so one CTA's
-//   softmax overlaps the other's MMAs.
+// attn64_kernel (head_dim 64, tcgen05 + TMA + TMEM): one CTA per (128-query tile, head); the work list
+// (sequence start, length, first query row per tile, longest sequences first) is built once per batch
+// by esmk_batch_meta, so no CTA is launched for padding.  Two CTAs per SM (80 KB smem, 256 TMEM columns each).
+//   warp 0     : TMA producer (Q once; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B, double-buffered)
+//   warp 1     : tcgen05.mma issuer:  S = Q K_j^T   (SS UMMA 128x128x16, K-major smem operands)
+//                                      O += P_j V_j  (TS UMMA 128x64x16: P read from TENSOR MEMORY, V MN-major smem)
+//   warps 2..9 : softmax, TWO threads per query row (each owns 64 of the block's 128 keys and 32 of the
+//                64 O columns): one TMEM read of S per block, row maximum exchanged through shared memory,
+//                P = exp2(S*c - m) rounded to bf16 and written back to TMEM (tcgen05.st).
+//   TMEM (256 columns): S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256)
+//   - S_{j+1} is issued as soon as the softmax warps hold S_j in registers (s_free), so it overlaps the
+//     exponentials of block j; no P staging in shared memory;
+//   - O accumulates in TMEM and is rescaled lazily: only when a row maximum grows by more than 2^8 over the
+//     reference maximum its P values were scaled with (P <= 256 keeps bf16's relative precision, row sums
+//     stay in fp32), so the steady state is bound by the exponentials (MUFU), not by corrections.
 //
-// attn_generic_kernel: CUDA-core kernel for other head dims (e.g. ESM2-8M, hd=16)
-//   and the on-device cross-check of the tcgen05 kernel.
+// attn_generic_kernel: CUDA-core kernel for other head dims (e.g. ESM2-8M, hd=16) and the on-device
+// cross-check of the tcgen05 kernel.
 //
-// Semantics follow flash_attn_varlen_func as called at esme/attention.py:115-123:
-// scale hd^-0.5, fp32 scores, un-normalised P rounded to bf16 before P.V, fp32 row
-// sums of the un-rounded P, one final rounding of O.
+// Semantics follow flash_attn_varlen_func as called at esme/attention.py:115-123: scale hd^-0.5, fp32
+// scores, un-normalised P rounded to bf16 before P.V, fp32 row sums of the un-rounded P, one final rounding.
 #include "common.cuh"
 #include "esmk_internal.h"
 
@@ -30,279 +34,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// ---------------------------------------------------------------------------
-// tcgen05 kernel, head_dim = 64
-// ---------------------------------------------------------------------------
-constexpr int AT_THREADS = 192;
-constexpr int TILE = 128;            // query rows per CTA == keys per block
+constexpr int TILE = 128;                  // query rows per CTA == keys per block
 constexpr int HD64 = 64;
 constexpr int Q_BYTES = TILE * HD64 * 2;   // 16 KB
-constexpr int P_BYTES = TILE * TILE * 2;   // 32 KB (two 128x64 swizzle atoms)
-constexpr int AT_SMEM = Q_BYTES * 3 + P_BYTES + 1024 + 128;
-constexpr int AT_TMEM_COLS = 256;    // S: [0,128)  O: [128,192)
-
-// One 128-key block of the online softmax for one query row (= one thread):
-// pass 1 reads S from TMEM for the row maximum, pass 2 re-reads it, forms P = exp2(S*c - m),
-// rounds to bf16 and writes the row into shared memory in the UMMA K-major SWIZZLE_128B layout.
-template <bool MASK>
-__device__ __forceinline__ void softmax_block(uint32_t t_row, uint8_t* prow, int rsw, int kv_valid, float scale_log2,
-                                              float& m_run, float& l_run, float& alpha) {
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t s[32];
-    tmem_ld32(t_row + c * 32, s);
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float x = __uint_as_float(s[i]);
-      mx = (!MASK || c * 32 + i < kv_valid) ? fmaxf(mx, x) : mx;
-    }
-  }
-  const float m_new = fmaxf(m_run, mx * scale_log2);
-  alpha = fast_exp2(m_run - m_new);  // m_run = -inf on the first block -> 0
-  float rowsum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t s[32];
-    tmem_ld32(t_row + c * 32, s);
-    tmem_wait_ld();
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -m_new));
-      float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_new));
-      if (MASK) {
-        p0 = (c * 32 + i < kv_valid) ? p0 : 0.f;
-        p1 = (c * 32 + i + 1 < kv_valid) ? p1 : 0.f;
-      }
-      rowsum += p0 + p1;
-      pk[i >> 1] = pack_bf16(p0, p1);
-    }
-    // keys [c*32, c*32+32) -> atom (c>>1), 16-byte chunks ((c&1)*4 .. +3) of this row, XOR-swizzled by row&7
-    uint8_t* atom = prow + (c >> 1) * (TILE * 128);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int chunk = ((c & 1) * 4 + q) ^ rsw;
-      *reinterpret_cast<uint4*>(atom + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    }
-  }
-  l_run = fmaf(l_run, alpha, rowsum);
-  m_run = m_new;
-}
-
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-              const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-              const int32_t* __restrict__ cu_lens, const int32_t* __restrict__ tile_cu, int B, float scale_log2) {
-  // ---- which (sequence, query tile) is this CTA? ----
-  const int tq = blockIdx.x;
-  if (tq >= tile_cu[B]) return;
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (tile_cu[mid] <= tq) lo = mid; else hi = mid;
-  }
-  const int seq_start = cu_lens[lo];
-  const int L = cu_lens[lo + 1] - seq_start;
-  const int q0 = (tq - tile_cu[lo]) * TILE;
-  const int n_kv = (L + TILE - 1) / TILE;
-  const int head = blockIdx.y;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + Q_BYTES;
-  uint8_t* sP = sV + Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(bar_q, 1);
-    mbar_init(k_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(k_empty, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, AT_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      const int col = head * HD64;
-      mbar_arrive_expect_tx(bar_q, Q_BYTES);
-      tma_load_2d(sQ, &tmQ, bar_q, col, seq_start + q0);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = j & 1;
-        const int krow = seq_start + j * TILE;
-        mbar_wait_backoff(k_empty, ph ^ 1);
-        mbar_arrive_expect_tx(k_full, Q_BYTES);
-        tma_load_2d(sK, &tmK, k_full, col, krow);
-        mbar_wait_backoff(v_empty, ph ^ 1);
-        mbar_arrive_expect_tx(v_full, Q_BYTES);
-        tma_load_2d(sV, &tmV, v_full, col, krow);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : V is MN-major
-      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, 1024, 2);
-      const uint64_t kdesc = make_smem_desc(smem_u32(sK), 16, 1024, 2);
-      const uint64_t vdesc = make_smem_desc(smem_u32(sV), 1024, 1024, 2);
-      const uint64_t pdesc0 = make_smem_desc(smem_u32(sP), 16, 1024, 2);
-      const uint64_t pdesc1 = make_smem_desc(smem_u32(sP + TILE * 128), 16, 1024, 2);
-
-      mbar_wait(bar_q, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      umma_commit(s_full);
-      umma_commit(k_empty);
-      for (int j = 0; j < n_kv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait_backoff(p_full, ph);
-        mbar_wait_backoff(v_full, ph);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < TILE / 16; ++k) {
-          // P: 16 keys = 32 bytes inside a 64-key swizzle atom; V: 16 key rows = 2048 bytes
-          const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-          umma_ss(tmem_O, pd, vdesc + (k * 2048 >> 4), idesc_o, k != 0);
-        }
-        umma_commit(o_full);
-        umma_commit(v_empty);
-        if (j + 1 < n_kv) {
-          mbar_wait_backoff(k_full, ph ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-          umma_commit(k_empty);
-        }
-      }
-    }
-  } else {
-    // ===================== softmax / accumulate =====================
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[HD64];
-#pragma unroll
-    for (int i = 0; i < HD64; ++i) acc[i] = 0.f;
-    uint8_t* prow = sP + r * 128;
-    const int rsw = r & 7;
-
-    for (int j = 0; j < n_kv; ++j) {
-      const uint32_t ph = j & 1;
-      const int kv_valid = L - j * TILE;  // keys [0, kv_valid) of this block exist (< TILE only in the last block)
-      mbar_wait(s_full, ph);
-      tc_fence_after();
-      float alpha;
-      if (kv_valid >= TILE) softmax_block<false>(tmem_S + lane_off, prow, rsw, TILE, scale_log2, m_run, l_run, alpha);
-      else softmax_block<true>(tmem_S + lane_off, prow, rsw, kv_valid, scale_log2, m_run, l_run, alpha);
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();         // our tcgen05.ld of S are complete before the MMA warp overwrites S
-      mbar_arrive(p_full);
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      {
-        uint32_t o0[32], o1[32];
-        tmem_ld32(tmem_O + lane_off, o0);
-        tmem_ld32(tmem_O + lane_off + 32, o1);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          acc[i] = fmaf(acc[i], alpha, __uint_as_float(o0[i]));
-          acc[32 + i] = fmaf(acc[32 + i], alpha, __uint_as_float(o1[i]));
-        }
-      }
-    }
-    if (q0 + r < L) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + head * HD64;
-#pragma unroll
-      for (int i = 0; i < HD64; i += 8)
-        *reinterpret_cast<uint4*>(dst + i) =
-            make_uint4(pack_bf16(acc[i] * inv, acc[i + 1] * inv), pack_bf16(acc[i + 2] * inv, acc[i + 3] * inv),
-                       pack_bf16(acc[i + 4] * inv, acc[i + 5] * inv), pack_bf16(acc[i + 6] * inv, acc[i + 7] * inv));
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// tcgen05 kernel v2, head_dim = 64: P and O stay in tensor memory.
-//   TMEM (256 columns): S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256)
-//   smem (80 KB):       Q | K x2 | V x2      (K and V double-buffered, no P staging)
-//   - S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax warps have pulled S_j out of TMEM
-//     (s_free), so it overlaps the exponentials of block j;
-//   - P_j is written back to TMEM (tcgen05.st) and consumed as the A operand of O += P_j V_j;
-//   - O accumulates in TMEM; it is only rescaled when a row maximum grows by more than 2^8
-//     relative to the reference maximum its P values were scaled with (lazy rescaling: P <= 256 keeps
-//     bf16's relative precision, row sums stay in fp32).
-// ---------------------------------------------------------------------------
-constexpr int A2_SMEM = Q_BYTES * 5 + 1024 + 128;
-constexpr float kRescaleThreshold = 8.0f;   // log2 units
-
-template <bool MASK>
-__device__ __forceinline__ float row_max64(uint32_t t_addr, int col0, int kv_valid) {
-  uint32_t a[32], b[32];
-  tmem_ld32(t_addr, a);
-  tmem_ld32(t_addr + 32, b);
-  tmem_wait_ld();
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float x0 = __uint_as_float(a[i]), x1 = __uint_as_float(a[i + 1]);
-    float y0 = __uint_as_float(b[i]), y1 = __uint_as_float(b[i + 1]);
-    if (MASK) {
-      x0 = (col0 + i < kv_valid) ? x0 : -INFINITY;
-      x1 = (col0 + i + 1 < kv_valid) ? x1 : -INFINITY;
-      y0 = (col0 + 32 + i < kv_valid) ? y0 : -INFINITY;
-      y1 = (col0 + 33 + i < kv_valid) ? y1 : -INFINITY;
-    }
-    m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1); m2 = fmaxf(m2, y0); m3 = fmaxf(m3, y1);
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
+constexpr int AT_TMEM_COLS = 256;
+constexpr int AT_THREADS = 64 + 256;
+constexpr int AT_SMEM = Q_BYTES * 5 + 1024 + 128 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
+                        2 * TILE * 4 /*row-sum exchange*/;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 // exp2(x*c - m) for 32 fp32 values (already in registers) -> 16 packed bf16x2 words; returns the fp32
 // sum of the un-rounded values
@@ -325,266 +64,16 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int col0, i
   return s0 + s1;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn64v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-                const int32_t* __restrict__ cu_lens, const int32_t* __restrict__ tile_cu, int B, float scale_log2) {
-  const int tq = blockIdx.x;
-  if (tq >= tile_cu[B]) return;
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (tile_cu[mid] <= tq) lo = mid; else hi = mid;
-  }
-  const int seq_start = cu_lens[lo];
-  const int L = cu_lens[lo + 1] - seq_start;
-  const int q0 = (tq - tile_cu[lo]) * TILE;
-  const int n_kv = (L + TILE - 1) / TILE;
-  const int head = blockIdx.y;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
-  uint8_t* sV = sK + 2 * Q_BYTES;      // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Q_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_free = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
-    mbar_init(o_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, AT_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_P = tmem_base + 128;
-  const uint32_t tmem_O = tmem_base + 192;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      const int col = head * HD64;
-      mbar_arrive_expect_tx(bar_q, Q_BYTES);
-      tma_load_2d(sQ, &tmQ, bar_q, col, seq_start + q0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int krow = seq_start + j * TILE;
-        mbar_wait_backoff(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
-        tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
-        mbar_wait_backoff(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
-        tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major from smem
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
-      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, 1024, 2);
-      mbar_wait_backoff(bar_q, 0);
-      mbar_wait_backoff(&k_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_smem_desc(smem_u32(sK), 16, 1024, 2);
-#pragma unroll
-        for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      }
-      umma_commit(s_full);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        if (j + 1 < n_kv) {
-          const int st1 = (j + 1) & 1;
-          const uint32_t ph1 = ((j + 1) >> 1) & 1;
-          mbar_wait_backoff(s_free, j & 1);           // S_j has been copied to registers
-          mbar_wait_backoff(&k_full[st1], ph1);
-          tc_fence_after();
-          const uint64_t kdesc = make_smem_desc(smem_u32(sK + st1 * Q_BYTES), 16, 1024, 2);
-#pragma unroll
-          for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-          umma_commit(&k_empty[st1]);
-        }
-        mbar_wait_backoff(p_full, j & 1);
-        mbar_wait_backoff(&v_full[st], ph);
-        tc_fence_after();
-        const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
-#pragma unroll
-        for (int k = 0; k < TILE / 16; ++k)   // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
-          umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
-        umma_commit(o_done);
-        umma_commit(&v_empty[st]);
-      }
-    }
-  } else {
-    // ===================== softmax warps: one query row per thread =====================
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_S + lane_off, tP = tmem_P + lane_off, tO = tmem_O + lane_off;
-    float m_ref = -INFINITY, l_run = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv_valid = L - j * TILE;
-      const bool masked = kv_valid < TILE;
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // ---- pass 1: row maximum ----
-      float mx = masked ? fmaxf(row_max64<true>(tS, 0, kv_valid), row_max64<true>(tS + 64, 64, kv_valid))
-                        : fmaxf(row_max64<false>(tS, 0, kv_valid), row_max64<false>(tS + 64, 64, kv_valid));
-      mx *= scale_log2;
-      bool o_waited = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const bool grow = mx > m_ref + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {          // warp-uniform: tcgen05.ld/st are warp-collective
-          const float m_new = grow ? mx : m_ref;
-          const float f = fast_exp2(m_ref - m_new);   // 1 for rows that keep their reference
-          mbar_wait(o_done, (j - 1) & 1);             // P_{j-1} V_{j-1} has landed in O
-          o_waited = true;
-          tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[32];
-            tmem_ld32(tO + h * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tO + h * 32, o);
-          }
-          tmem_wait_st();
-          l_run *= f;
-          m_ref = m_new;
-        }
-      }
-      // ---- pass 2: pull the whole S row into registers, release S, then P = exp2(S*c - m_ref) ----
-      uint32_t sa[32], sb[32], sc[32], sd[32];
-      tmem_ld32(tS, sa);
-      tmem_ld32(tS + 32, sb);
-      tmem_ld32(tS + 64, sc);
-      tmem_ld32(tS + 96, sd);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(s_free);                            // the MMA warp may now overwrite S with Q K_{j+1}^T
-      uint32_t pk0[32], pk1[32];
-      float rowsum;
-      if (masked) {
-        rowsum = exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk0) +
-                 exp_pack32<true>(sb, 32, kv_valid, scale_log2, m_ref, pk0 + 16);
-        rowsum += exp_pack32<true>(sc, 64, kv_valid, scale_log2, m_ref, pk1) +
-                  exp_pack32<true>(sd, 96, kv_valid, scale_log2, m_ref, pk1 + 16);
-      } else {
-        rowsum = exp_pack32<false>(sa, 0, kv_valid, scale_log2, m_ref, pk0) +
-                 exp_pack32<false>(sb, 32, kv_valid, scale_log2, m_ref, pk0 + 16);
-        rowsum += exp_pack32<false>(sc, 64, kv_valid, scale_log2, m_ref, pk1) +
-                  exp_pack32<false>(sd, 96, kv_valid, scale_log2, m_ref, pk1 + 16);
-      }
-      l_run += rowsum;
-      if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      tmem_st32(tP, pk0);
-      tmem_st32(tP + 32, pk1);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // ---- epilogue: O / l -> bf16 -> global ----
-    mbar_wait(o_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.0f / l_run;
-    const bool row_ok = q0 + r < L;
-    __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + head * HD64;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t o[32];
-      tmem_ld32(tO + h * 32, o);
-      tmem_wait_ld();
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dst + h * 32 + i) = make_uint4(
-              pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// tcgen05 kernel v3, head_dim = 64: v2's dataflow (P and O in tensor memory, lazy rescale) with TWO
-// threads per query row -- 8 softmax warps per CTA, 16 per SM -- so the exponentials (MUFU) and their
-// dependent chains are covered by four warps per scheduler instead of two.  Thread (row r, half hf)
-// owns key columns [64 hf, 64 hf + 64) of its row: one TMEM read of S per block (64 values stay in
-// registers), the row maximum is exchanged with the partner thread through shared memory, row sums stay
-// per-thread partials until the epilogue, and each half rescales / normalises 32 of the 64 O columns.
-// ---------------------------------------------------------------------------
-constexpr int A3_THREADS = 64 + 256;
-constexpr int A3_SMEM = Q_BYTES * 5 + 1024 + 128 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
-                        2 * TILE * 4 /*row-sum exchange*/;
-
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(A3_THREADS, 2)
-attn64v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-                const int32_t* __restrict__ cu_lens, const int32_t* __restrict__ tile_cu, int B, float scale_log2) {
-  const int tq = blockIdx.x;
-  if (tq >= tile_cu[B]) return;
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (tile_cu[mid] <= tq) lo = mid; else hi = mid;
-  }
-  const int seq_start = cu_lens[lo];
-  const int L = cu_lens[lo + 1] - seq_start;
-  const int q0 = (tq - tile_cu[lo]) * TILE;
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
+              const int4* __restrict__ tile_info, float scale_log2) {
+  // work item: {first packed row of the sequence, sequence length, first query row of this tile, -}
+  const int4 info = __ldg(tile_info + blockIdx.x);
+  const int seq_start = info.x, L = info.y, q0 = info.z;
+  if (L <= 0) return;                      // unused slot of the (upper-bound sized) work list
   const int n_kv = (L + TILE - 1) / TILE;
   const int head = blockIdx.y;
 
@@ -897,13 +386,14 @@ attn_generic_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 }  // namespace
 
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
-                const int32_t* tile_cu, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st) {
+                const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st) {
   ESMK_REQUIRE(B >= 1 && T >= 1 && H >= 1, "empty attention problem");
   ESMK_REQUIRE(hd % 8 == 0 && hd <= 128, "head_dim must be a multiple of 8 and <= 128");
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
   const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
-  if (hd == 64 && (impl == 0 || impl == 2 || impl == 3)) {
-    ESMK_REQUIRE(tile_cu != nullptr, "tile_cu (esmk_batch_meta) required");
+  if (hd == 64 && impl == 0) {
+    ESMK_REQUIRE(tile_info != nullptr, "tile_info (esmk_batch_meta) required");
+    ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");
     CUtensorMap tq, tk, tv;
     ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
@@ -911,20 +401,11 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     static bool configured = false;
     if (!configured) {
       ESMK_CUDA(cudaFuncSetAttribute(attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      ESMK_CUDA(cudaFuncSetAttribute(attn64v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-      ESMK_CUDA(cudaFuncSetAttribute(attn64v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM));
       configured = true;
     }
-    dim3 grid((T + TILE - 1) / TILE + B, H);
-    if (impl == 0)
-      attn64v3_kernel<<<grid, A3_THREADS, A3_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
-                                                          scale_log2);
-    else if (impl == 3)
-      attn64v2_kernel<<<grid, AT_THREADS, A2_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
-                                                          scale_log2);
-    else
-      attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo, cu_lens, tile_cu, B,
-                                                        scale_log2);
+    dim3 grid(tile_capacity(T, B), H);
+    attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
+                                                      reinterpret_cast<const int4*>(tile_info), scale_log2);
   } else {
     dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
     attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,

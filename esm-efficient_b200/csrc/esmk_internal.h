@@ -13,7 +13,8 @@ const std::string& last_error();
 void count_launch(int n = 1);
 uint64_t launch_count();
 
-int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, cudaStream_t st);
+int tile_capacity(int T, int B);
+int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_info, cudaStream_t st);
 int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st);
 int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
           const uint8_t* zero_rows, cudaStream_t st);
@@ -26,7 +27,7 @@ int softmax(const void* x, int ldx, void* y, int ldy, int T, int V, int log_mode
 int gemm(const esmk_gemm_args& a, cudaStream_t st);
 
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
-                const int32_t* tile_cu, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st);
+                const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st);
 
 void profile_enable(int on);
 int profile_read(float* ms, int* launches, int n_categories);

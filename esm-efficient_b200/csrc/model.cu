@@ -72,7 +72,7 @@ struct Workspace {
 
 struct Buffers {
   __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb;
-  int32_t *pos, *tile_cu;
+  int32_t *pos, *tile_info;
   size_t bytes;
 };
 
@@ -88,7 +88,7 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len) {
   b.cosb = w.take<__nv_bfloat16>((size_t)max_len * hd);
   b.sinb = w.take<__nv_bfloat16>((size_t)max_len * hd);
   b.pos = w.take<int32_t>((size_t)T);
-  b.tile_cu = w.take<int32_t>((size_t)B + 1);
+  b.tile_info = w.take<int32_t>((size_t)4 * tile_capacity(T, B));
   b.bytes = w.off;
   return b;
 }
@@ -185,7 +185,7 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
   const float s = c.residue_scaling;
   const bool fused_rope = (c.family == 0) && (hd <= 64) && ((2 * D) % 64 == 0);
 
-  PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_cu, st));
+  PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_info, st));
   PROF(ESMK_PROF_MISC, rope_tables(b.cosb, b.sinb, max_len, hd, st));
   // esme/esm.py:188-189: ESM2 zeroes <mask>(32) rows; ESMC (esm.py:876) does not
   PROF(ESMK_PROF_MISC, embed(tokens, m->w.embed, b.x, T, D, c.embed_rows, c.family == 0 ? 32 : -1, zero_rows, st));
@@ -205,7 +205,7 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
       PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
     }
     PROF(ESMK_PROF_ATTENTION,
-         attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_cu, B, T, H, hd, max_len, 0, st));
+         attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));
     PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, l.wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)
     PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));

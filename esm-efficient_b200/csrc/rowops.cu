@@ -28,34 +28,68 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------
-// batch metadata
+// batch metadata (once per batch; the reference recomputes positions twice per layer with host syncs,
+// esme/rotary.py:5-14)
+//   pos[t]        = t - cu_lens[seq(t)]
+//   tile_info[i]  = {first packed row of the sequence, sequence length, first query row of the tile, sequence id}
+//                   for every 128-query tile of every sequence, longest sequences first (LPT order keeps
+//                   the attention grid's tail short); unused slots up to tile_capacity(T, B) have length 0.
 // ---------------------------------------------------------------------------
-__global__ void batch_meta_kernel(const int32_t* __restrict__ cu, int B, int T, int32_t* __restrict__ pos,
-                                  int32_t* __restrict__ tile_cu) {
+__global__ void positions_kernel(const int32_t* __restrict__ cu, int B, int T, int32_t* __restrict__ pos) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0 && tile_cu != nullptr) {
-    int acc = 0;
-    tile_cu[0] = 0;
-    for (int s = 0; s < B; ++s) {
-      acc += (cu[s + 1] - cu[s] + 127) >> 7;
-      tile_cu[s + 1] = acc;
-    }
+  if (t >= T) return;
+  int lo = 0, hi = B;  // find s with cu[s] <= t < cu[s+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cu[mid] <= t) lo = mid; else hi = mid;
   }
-  if (t < T && pos != nullptr) {
-    int lo = 0, hi = B;  // find s with cu[s] <= t < cu[s+1]
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (cu[mid] <= t) lo = mid; else hi = mid;
-    }
-    pos[t] = t - cu[lo];
-  }
+  pos[t] = t - cu[lo];
 }
 
-int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, cudaStream_t st) {
+constexpr int kTileBuckets = 64;   // sequences are bucketed by min(number of tiles, 64)
+
+__global__ void __launch_bounds__(1024)
+tile_list_kernel(const int32_t* __restrict__ cu, int B, int capacity, int4* __restrict__ tile_info) {
+  __shared__ int hist[kTileBuckets + 1];    // tiles per bucket
+  __shared__ int cursor[kTileBuckets + 1];  // next free slot per bucket
+  const int tid = threadIdx.x;
+  if (tid <= kTileBuckets) hist[tid] = 0;
+  __syncthreads();
+  for (int s = tid; s < B; s += blockDim.x) {
+    const int n = (cu[s + 1] - cu[s] + 127) >> 7;
+    if (n > 0) atomicAdd(&hist[n < kTileBuckets ? n : kTileBuckets], n);
+  }
+  __syncthreads();
+  if (tid == 0) {                           // slots handed out from the longest bucket down
+    int acc = 0;
+    for (int b = kTileBuckets; b >= 1; --b) { cursor[b] = acc; acc += hist[b]; }
+    cursor[0] = acc;                        // total number of tiles
+  }
+  __syncthreads();
+  const int total = cursor[0];
+  for (int s = tid; s < B; s += blockDim.x) {
+    const int start = cu[s], len = cu[s + 1] - start;
+    const int n = (len + 127) >> 7;
+    if (n == 0) continue;
+    const int base = atomicAdd(&cursor[n < kTileBuckets ? n : kTileBuckets], n);
+    for (int i = 0; i < n; ++i) tile_info[base + i] = make_int4(start, len, i * 128, s);
+  }
+  for (int i = total + tid; i < capacity; i += blockDim.x) tile_info[i] = make_int4(0, 0, 0, -1);
+}
+
+int tile_capacity(int T, int B) { return (T + 127) / 128 + B; }
+
+int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_info, cudaStream_t st) {
   ESMK_REQUIRE(B >= 1 && T >= 1, "empty batch");
-  int threads = 256;
-  batch_meta_kernel<<<(T + threads - 1) / threads, threads, 0, st>>>(cu_lens, B, T, pos, tile_cu);
-  count_launch();
+  if (pos != nullptr) {
+    positions_kernel<<<(T + 255) / 256, 256, 0, st>>>(cu_lens, B, T, pos);
+    count_launch();
+  }
+  if (tile_info != nullptr) {
+    ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");
+    tile_list_kernel<<<1, 1024, 0, st>>>(cu_lens, B, tile_capacity(T, B), reinterpret_cast<int4*>(tile_info));
+    count_launch();
+  }
   ESMK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -91,7 +91,7 @@ class FlashMultiheadAttention(nn.Module):
         T = x.shape[0]
         h = ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         w, b = self.packed_qkv()
-        pos, tile_cu = ops.batch_meta(cu_lens, T)
+        pos, tile_info = ops.batch_meta(cu_lens, T)
         cos = sin = None
         if self.rot_emb is not None:
             self.rot_emb._update_cos_sin_cache(max_len, device=x.device, dtype=x.dtype)
@@ -105,18 +105,18 @@ class FlashMultiheadAttention(nn.Module):
                 ops.qk_norm_rope_(qkv[:, :D], qkv[:, D:2 * D], H, hd,
                                   self.layernorm_q.weight if self.pre_layernorm else None,
                                   self.layernorm_k.weight if self.pre_layernorm else None, cos, sin, pos)
-        return qkv, tile_cu
+        return qkv, tile_info
 
-    def _attn(self, qkv: Tensor, cu_lens: Tensor, max_len: int, tile_cu=None) -> Tensor:
+    def _attn(self, qkv: Tensor, cu_lens: Tensor, max_len: int, tile_info=None) -> Tensor:
         T = qkv.shape[0]
         D, H, hd = self.embed_dim, self.num_heads, self.head_dim
         q, k, v = (qkv[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
-        return ops.attn_varlen(q, k, v, cu_lens, max_len, tile_cu)
+        return ops.attn_varlen(q, k, v, cu_lens, max_len, tile_info)
 
     def forward(self, x: Tensor, cu_lens, max_len, lora_names=None) -> Tensor:
         _reject_lora(lora_names)
-        qkv, tile_cu = self._qkv_rot(x, cu_lens, max_len)
-        a = self._attn(qkv, cu_lens, max_len, tile_cu)
+        qkv, tile_info = self._qkv_rot(x, cu_lens, max_len)
+        a = self._attn(qkv, cu_lens, max_len, tile_info)
         return ops.linear(a, self.out.weight, self.out.bias)
 
 
@@ -155,8 +155,8 @@ class FlashTransformerLayer(nn.Module):
     def forward(self, x: Tensor, cu_lens, max_len, lora_names=None) -> Tensor:
         _reject_lora(lora_names)
         sa, s = self.self_attn, float(self.residue_scaling)
-        qkv, tile_cu = sa._qkv_rot(x, cu_lens, max_len)
-        a = sa._attn(qkv, cu_lens, max_len, tile_cu)
+        qkv, tile_info = sa._qkv_rot(x, cu_lens, max_len)
+        a = sa._attn(qkv, cu_lens, max_len, tile_info)
         # x + out(a) / s, fused into the out-projection epilogue
         x = ops.linear(a, sa.out.weight, sa.out.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
         ln = self.final[0]

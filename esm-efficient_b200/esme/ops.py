@@ -37,15 +37,17 @@ def _rows(t: torch.Tensor) -> Tuple[int, int]:
 
 
 def batch_meta(cu_lens: torch.Tensor, T: int):
-    """-> (pos int32[T], tile_cu int32[B+1]); replaces esme/rotary.py:5-14 culen_indices."""
+    """-> (pos int32[T], tile_info int32[capacity, 4]): per-token positions (replaces esme/rotary.py:5-14
+    culen_indices) and the attention work list, one {seq start, seq length, first query row, seq id}
+    record per 128-query tile, longest sequences first."""
     _need_cuda(cu_lens)
     assert cu_lens.dtype == torch.int32 and cu_lens.is_contiguous()
     B = cu_lens.numel() - 1
     pos = torch.empty(T, dtype=torch.int32, device=cu_lens.device)
-    tile_cu = torch.empty(B + 1, dtype=torch.int32, device=cu_lens.device)
-    L.check(L.lib.esmk_batch_meta(cu_lens.data_ptr(), B, T, pos.data_ptr(), tile_cu.data_ptr(), _stream()),
+    tile_info = torch.empty(L.lib.esmk_tile_capacity(T, B), 4, dtype=torch.int32, device=cu_lens.device)
+    L.check(L.lib.esmk_batch_meta(cu_lens.data_ptr(), B, T, pos.data_ptr(), tile_info.data_ptr(), _stream()),
             'esmk_batch_meta')
-    return pos, tile_cu
+    return pos, tile_info
 
 
 def rope_tables(max_len: int, head_dim: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -141,7 +143,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torch.Tensor, max_len: int,
-                tile_cu: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
+                tile_info: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
     """q,k,v: [T,H,hd] views with a common row pitch (e.g. column blocks of the QKV
     GEMM output) -> [T, H*hd].  Replaces flash_attn_varlen_func (esme/attention.py:115)."""
     _need_cuda(q, k, v, cu_lens)
@@ -152,10 +154,10 @@ def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torc
     assert k.stride(0) == ld and v.stride(0) == ld
     assert cu_lens.dtype == torch.int32
     B = cu_lens.numel() - 1
-    if tile_cu is None:
-        _, tile_cu = batch_meta(cu_lens, T)
+    if tile_info is None:
+        _, tile_info = batch_meta(cu_lens, T)
     out = torch.empty(T, H * hd, dtype=bf16, device=q.device)
     L.check(L.lib.esmk_attn_varlen(q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, out.data_ptr(), H * hd,
-                                   cu_lens.data_ptr(), tile_cu.data_ptr(), B, T, H, hd, int(max_len), impl,
+                                   cu_lens.data_ptr(), tile_info.data_ptr(), B, T, H, hd, int(max_len), impl,
                                    _stream()), 'esmk_attn_varlen')
     return out

@@ -41,13 +41,16 @@ ESMK_API int esmk_version(void);
 ESMK_API uint64_t esmk_launch_count(void);
 
 /* ---- batch metadata ---------------------------------------------------- */
-/* Per-token position inside its own sequence and q-tile prefix sums.
- * Replaces esme/rotary.py:5-14 `culen_indices` (which the reference recomputes,
- * with host syncs, twice per layer); computed once per batch here.
- *   cu_lens  int32[B+1]          (device)
- *   pos      int32[T]            out: t - cu_lens[seq(t)]
- *   tile_cu  int32[B+1]          out: prefix sum of ceil(L_s / 128) (attention work list) */
-ESMK_API int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_cu, esmk_stream_t stream);
+/* Per-token position inside its own sequence and the attention work list, computed once per batch.
+ * Replaces esme/rotary.py:5-14 `culen_indices` (which the reference recomputes, with host syncs,
+ * twice per layer).
+ *   cu_lens    int32[B+1]                            (device)
+ *   pos        int32[T]   out (may be NULL): t - cu_lens[seq(t)]
+ *   tile_info  int32[4 * esmk_tile_capacity(T, B)]  out (may be NULL), 16-byte aligned: one
+ *              {sequence start row, sequence length, first query row of the tile, sequence id} record
+ *              per 128-query tile, longest sequences first; unused records have length 0. */
+ESMK_API int esmk_tile_capacity(int T, int B);
+ESMK_API int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_info, esmk_stream_t stream);
 
 /* cos/sin tables, esme/rotary.py:116-149: fp32 angle = p * 10000^(-2i/hd), table row = [f, f],
  * cast to bf16.  cos, sin: bf16 [max_len, hd]. */
@@ -116,11 +119,11 @@ ESMK_API int esmk_gemm(const esmk_gemm_args* args, esmk_stream_t stream);
  *   q,k,v : bf16, token t / head h at  ptr + t*ld + h*hd   (e.g. three column
  *           blocks of one [T,3D] QKV GEMM output, ld = 3D)
  *   out   : bf16 [T, H*hd], pitch ldo
- *   tile_cu from esmk_batch_meta.
+ *   tile_info from esmk_batch_meta (required for head_dim 64).
  * head_dim == 64 runs the tcgen05/TMA kernel; other head dims (<=128, multiple of 8)
  * run a CUDA-core kernel.  impl: 0 = auto, 1 = force the CUDA-core kernel. */
 ESMK_API int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo,
-                     const int32_t* cu_lens, const int32_t* tile_cu, int B, int T, int H, int head_dim,
+                     const int32_t* cu_lens, const int32_t* tile_info, int B, int T, int H, int head_dim,
                      int max_len, int impl, esmk_stream_t stream);
 
 /* ---- whole model --------------------------------------------------------- */

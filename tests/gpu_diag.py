@@ -251,15 +251,6 @@ def attn64_small():
 
 
 @case
-def attn64_v1():
-    out = {}
-    for name, lens in (('one_tile', [128]), ('ragged', [300, 131, 66, 2, 129, 257, 1]), ('long', [1026, 700, 3, 513])):
-        got, want = _attn_case(lens, 3, 64, impl=2, qk_scale=1.5)
-        _cmp(f'attn64v1_{name}', got, want, out)
-    return out
-
-
-@case
 def attn64_rescale():
     """Scores whose row maximum keeps growing by > 2^8 block after block: exercises the lazy O rescale."""
     torch, ops, L, O = _imports()
@@ -307,7 +298,7 @@ def attn_accuracy():
     exact = O.varlen_attention(q, k, v, cu, p64).reshape(T, D)
     qd = qkv.to(dev)
     a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
-    for name, impl in (('v3_tmem_2thr', 0), ('v2_tmem', 3), ('v1_smem', 2), ('generic', 1)):
+    for name, impl in (('tcgen05', 0), ('generic', 1)):
         _cmp(name, ops.attn_varlen(a, b, c, cu.to(dev), max(lens), impl=impl), exact, out)
     _cmp('oracle_bf16', O.varlen_attention(q.float(), k.float(), v.float(), cu, O._Prec('bf16')).reshape(T, D), exact, out)
     _cmp('exact_rounded_to_bf16', exact.bfloat16(), exact, out)
@@ -335,7 +326,7 @@ def perf_attn():
     qkv = torch.randn(T, 3 * D, device=dev).bfloat16()
     q, k, v = (qkv[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
     flops = 4.0 * D * sum(l * l for l in lens)
-    _, tile_cu = ops.batch_meta(cu, T)
+    _, tile_info = ops.batch_meta(cu, T)
 
     def timeit(fn, n=10):
         for _ in range(3):
@@ -348,15 +339,15 @@ def perf_attn():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
-    for name, impl in (('v3_tmem_2thr', 0), ('v2_tmem', 3), ('v1_smem', 2)):
-        ms = timeit(lambda: ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=impl))
+    for name, impl in (('tcgen05', 0),):
+        ms = timeit(lambda: ops.attn_varlen(q, k, v, cu, max(lens), tile_info, impl=impl))
         out[name] = dict(ms=ms, tflops=flops / ms / 1e9)
     try:
         from flash_attn import flash_attn_varlen_func
         qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
         ms = timeit(lambda: flash_attn_varlen_func(qc, kc, vc, cu, cu, max(lens), max(lens)))
         out['flash_attn_2.8.3_library'] = dict(ms=ms, tflops=flops / ms / 1e9)
-        a = ops.attn_varlen(q, k, v, cu, max(lens), tile_cu, impl=0).float()
+        a = ops.attn_varlen(q, k, v, cu, max(lens), tile_info, impl=0).float()
         b = flash_attn_varlen_func(qc, kc, vc, cu, cu, max(lens), max(lens)).reshape(T, D).float()
         out['v3_vs_flash_attn_max_abs'] = (a - b).abs().max().item()
     except Exception as e:                                  # library baseline is optional

@@ -71,6 +71,11 @@ def test_attention_kernels_agree_and_are_batch_invariant():
     cu = torch.tensor([0, 200, 331, 846], dtype=torch.int32, device=dev)
     q, k, v = (qkv[:, i * H * hd:(i + 1) * H * hd].unflatten(1, (H, hd)) for i in range(3))
     a = ops.attn_varlen(q, k, v, cu, max(lens), impl=0)
+    _, info = ops.batch_meta(cu, T)
+    rec = info.cpu()
+    live = rec[rec[:, 1] > 0]
+    assert live.shape[0] == sum((l + 127) // 128 for l in lens)            # one record per 128-query tile
+    assert live[:, 1].tolist() == sorted(live[:, 1].tolist(), reverse=True)  # longest sequences first
     b = ops.attn_varlen(q, k, v, cu, max(lens), impl=1)
     assert (a.float() - b.float()).abs().max().item() <= 2e-2
     # middle sequence alone
