@@ -2,8 +2,10 @@
 //
 // attn64_kernel (head_dim 64, tcgen05 + TMA + TMEM): one CTA per (128-query tile, head); the work list
 // (sequence start, length, first query row per tile, longest sequences first) is built once per batch
-// by esmk_batch_meta, so no CTA is launched for padding.  Two CTAs per SM (80 KB smem, 256 TMEM columns each).
-//   warp 0     : TMA producer (Q once; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B, double-buffered)
+// by esmk_batch_meta, so no CTA is launched for padding.  Two CTAs per SM (99 KB smem, 256 TMEM columns each).
+//   Each CTA walks up to 4 consecutive heads of its query tile so that the Q/K loads and the first S of
+//   head h+1 are in flight while the softmax warps finish head h (per-CTA start-up amortised).
+//   warp 0     : TMA producer (Q per head; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B, all double-buffered)
 //   warp 1     : tcgen05.mma issuer:  S = Q K_j^T   (SS UMMA 128x128x16, K-major smem operands)
 //                                      O += P_j V_j  (TS UMMA 128x64x16: P read from TENSOR MEMORY, V MN-major smem)
 //   warps 2..9 : softmax, TWO threads per query row (each owns 64 of the block's 128 keys and 32 of the
@@ -21,6 +23,8 @@
 //
 // Semantics follow flash_attn_varlen_func as called at esme/attention.py:115-123: scale hd^-0.5, fp32
 // scores, un-normalised P rounded to bf16 before P.V, fp32 row sums of the un-rounded P, one final rounding.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "esmk_internal.h"
 
@@ -39,7 +43,7 @@ constexpr int HD64 = 64;
 constexpr int Q_BYTES = TILE * HD64 * 2;   // 16 KB
 constexpr int AT_TMEM_COLS = 256;
 constexpr int AT_THREADS = 64 + 256;
-constexpr int AT_SMEM = Q_BYTES * 5 + 1024 + 128 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
+constexpr int AT_SMEM = Q_BYTES * 6 + 1024 + 192 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
                         2 * TILE * 4 /*row-sum exchange*/;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -69,31 +73,36 @@ __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-              const int4* __restrict__ tile_info, float scale_log2) {
+              const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2) {
   // work item: {first packed row of the sequence, sequence length, first query row of this tile, -}
   const int4 info = __ldg(tile_info + blockIdx.x);
   const int seq_start = info.x, L = info.y, q0 = info.z;
   if (L <= 0) return;                      // unused slot of the (upper-bound sized) work list
   const int n_kv = (L + TILE - 1) / TILE;
-  const int head = blockIdx.y;
+  // this CTA walks `nh` consecutive heads of the same query tile: the producer and the MMA warp run ahead
+  // into the next head while the softmax warps finish the current one, hiding the Q/K load and first-S latency
+  const int head0 = blockIdx.y * heads_per_cta;
+  const int nh = min(heads_per_cta, H - head0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
+  uint8_t* sQ = smem;                  // 2 stages (one per head in flight)
+  uint8_t* sK = sQ + 2 * Q_BYTES;      // 2 stages
   uint8_t* sV = sK + 2 * Q_BYTES;      // 2 stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Q_BYTES);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_free = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_done = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  float* x_max = reinterpret_cast<float*>(bars + 16);   // [2 parity][2 half][TILE]
+  uint64_t* q_full = bars + 0;   // [2]
+  uint64_t* q_empty = bars + 2;  // [2]
+  uint64_t* k_full = bars + 4;   // [2]
+  uint64_t* k_empty = bars + 6;  // [2]
+  uint64_t* v_full = bars + 8;   // [2]
+  uint64_t* v_empty = bars + 10; // [2]
+  uint64_t* s_full = bars + 12;
+  uint64_t* s_free = bars + 13;
+  uint64_t* p_full = bars + 14;
+  uint64_t* o_done = bars + 15;
+  uint64_t* o_free = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* x_max = reinterpret_cast<float*>(bars + 20);   // [2 parity][2 half][TILE]
   float* x_sum = x_max + 4 * TILE;                       // [2 half][TILE]
 
   const int warp = threadIdx.x >> 5;
@@ -103,8 +112,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(bar_q, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
@@ -114,6 +124,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     mbar_init(s_free, 256);
     mbar_init(p_full, 256);
     mbar_init(o_done, 1);
+    mbar_init(o_free, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -128,22 +139,29 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t tmem_P = tmem_base + 128;
   const uint32_t tmem_O = tmem_base + 192;
 
+  // `it` counts key blocks across all heads of this CTA: K/V stage = it & 1, stage phase = (it >> 1) & 1,
+  // and the per-block barriers (s_full, s_free, p_full, o_done) complete once per block -> parity it & 1.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const int col = head * HD64;
-      mbar_arrive_expect_tx(bar_q, Q_BYTES);
-      tma_load_2d(sQ, &tmQ, bar_q, col, seq_start + q0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int krow = seq_start + j * TILE;
-        mbar_wait_backoff(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
-        tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
-        mbar_wait_backoff(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
-        tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
+      int it = 0;
+      for (int hi = 0; hi < nh; ++hi) {
+        const int col = (head0 + hi) * HD64;
+        const int qs = hi & 1;
+        mbar_wait_backoff(&q_empty[qs], ((hi >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qs], Q_BYTES);
+        tma_load_2d(sQ + qs * Q_BYTES, &tmQ, &q_full[qs], col, seq_start + q0);
+        for (int j = 0; j < n_kv; ++j, ++it) {
+          const int st = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          const int krow = seq_start + j * TILE;
+          mbar_wait_backoff(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
+          tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
+          mbar_wait_backoff(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
+          tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
+        }
       }
     }
   } else if (warp == 1) {
@@ -151,41 +169,44 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major from smem
       constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
-      const uint64_t qdesc = make_smem_desc(smem_u32(sQ), 16, 1024, 2);
-      mbar_wait_backoff(bar_q, 0);
-      mbar_wait_backoff(&k_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = make_smem_desc(smem_u32(sK), 16, 1024, 2);
+      auto issue_s = [&](int qs, int blk) {                             // S = Q[qs] . K[blk & 1]^T
+        const int st = blk & 1;
+        mbar_wait_backoff(&k_full[st], (blk >> 1) & 1);
+        tc_fence_after();
+        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * Q_BYTES), 16, 1024, 2);
+        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * Q_BYTES), 16, 1024, 2);
 #pragma unroll
         for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-      }
-      umma_commit(s_full);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        if (j + 1 < n_kv) {
-          const int st1 = (j + 1) & 1;
-          const uint32_t ph1 = ((j + 1) >> 1) & 1;
-          mbar_wait_backoff(s_free, j & 1);           // S_j has been copied to registers
-          mbar_wait_backoff(&k_full[st1], ph1);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      };
+      int it = 0;
+      for (int hi = 0; hi < nh; ++hi) {
+        const int qs = hi & 1;
+        mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
+        if (it > 0) mbar_wait_backoff(s_free, (it - 1) & 1);            // previous head's last S is in registers
+        issue_s(qs, it);
+        if (n_kv == 1) umma_commit(&q_empty[qs]);
+        for (int j = 0; j < n_kv; ++j) {
+          const int cur = it + j;
+          const int st = cur & 1;
+          if (j + 1 < n_kv) {
+            mbar_wait_backoff(s_free, cur & 1);                          // S_j has been copied to registers
+            issue_s(qs, cur + 1);
+            if (j + 2 == n_kv) umma_commit(&q_empty[qs]);                // last S of this head: Q slot reusable
+          }
+          mbar_wait_backoff(p_full, cur & 1);
+          mbar_wait_backoff(&v_full[st], (cur >> 1) & 1);
+          if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
-          const uint64_t kdesc = make_smem_desc(smem_u32(sK + st1 * Q_BYTES), 16, 1024, 2);
+          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
 #pragma unroll
-          for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-          umma_commit(&k_empty[st1]);
+          for (int k = 0; k < TILE / 16; ++k)   // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
+            umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
+          umma_commit(o_done);
+          umma_commit(&v_empty[st]);
         }
-        mbar_wait_backoff(p_full, j & 1);
-        mbar_wait_backoff(&v_full[st], ph);
-        tc_fence_after();
-        const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
-#pragma unroll
-        for (int k = 0; k < TILE / 16; ++k)   // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
-          umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
-        umma_commit(o_done);
-        umma_commit(&v_empty[st]);
+        it += n_kv;
       }
     }
   } else {
@@ -197,107 +218,113 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tS = tmem_S + lane_off + hf * 64;
     const uint32_t tP = tmem_P + lane_off + hf * 32;
     const uint32_t tO = tmem_O + lane_off + hf * 32;
-    float m_ref = -INFINITY, l_part = 0.f;
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv_valid = L - j * TILE - hf * 64;   // valid keys among this thread's 64 columns
-      const bool masked = kv_valid < 64;
-      mbar_wait(s_full, j & 1);
+    int it = 0;
+    for (int hi = 0; hi < nh; ++hi) {
+      float m_ref = -INFINITY, l_part = 0.f;
+      for (int j = 0; j < n_kv; ++j) {
+        const int cur = it + j;
+        const int kv_valid = L - j * TILE - hf * 64;   // valid keys among this thread's 64 columns
+        const bool masked = kv_valid < 64;
+        mbar_wait(s_full, cur & 1);
+        tc_fence_after();
+        uint32_t sa[32], sb[32];
+        tmem_ld32(tS, sa);
+        tmem_ld32(tS + 32, sb);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(s_free);                            // both halves arrived -> S may be overwritten
+        // ---- row maximum of this half, exchanged with the partner thread ----
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, i < kv_valid ? __uint_as_float(sa[i]) : -INFINITY);
+            m1 = fmaxf(m1, i + 1 < kv_valid ? __uint_as_float(sa[i + 1]) : -INFINITY);
+            m2 = fmaxf(m2, 32 + i < kv_valid ? __uint_as_float(sb[i]) : -INFINITY);
+            m3 = fmaxf(m3, 33 + i < kv_valid ? __uint_as_float(sb[i + 1]) : -INFINITY);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            m0 = fmaxf(m0, __uint_as_float(sa[i]));
+            m1 = fmaxf(m1, __uint_as_float(sa[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sb[i]));
+            m3 = fmaxf(m3, __uint_as_float(sb[i + 1]));
+          }
+        }
+        float* xm = x_max + (cur & 1) * 2 * TILE;
+        const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        xm[hf * TILE + r] = mine;
+        softmax_bar();
+        const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
+        bool o_waited = false;
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          const bool grow = mx > m_ref + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {          // same rows, same decision in the partner warp
+            const float m_new = grow ? mx : m_ref;
+            const float f = fast_exp2(m_ref - m_new);
+            mbar_wait(o_done, (cur - 1) & 1);
+            o_waited = true;
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t o[16];
+              tmem_ld16(tO + h * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st16(tO + h * 16, o);
+            }
+            tmem_wait_st();
+            l_part *= f;
+            m_ref = m_new;
+          }
+        }
+        // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM (two 16-column stores keep the register peak low) ----
+        if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
+          mbar_wait(o_done, (cur - 1) & 1);             // (j == 0: the previous head's epilogue already waited)
+          tc_fence_after();
+        }
+        {
+          uint32_t pk[16];
+          l_part += masked ? exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk)
+                           : exp_pack32<false>(sa, 0, kv_valid, scale_log2, m_ref, pk);
+          tmem_st16(tP, pk);
+        }
+        {
+          uint32_t pk[16];
+          l_part += masked ? exp_pack32<true>(sb, 32, kv_valid, scale_log2, m_ref, pk)
+                           : exp_pack32<false>(sb, 32, kv_valid, scale_log2, m_ref, pk);
+          tmem_st16(tP + 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full);
+      }
+      it += n_kv;
+      // ---- head epilogue: total row sum, then O / l for this thread's 32 columns ----
+      x_sum[hf * TILE + r] = l_part;
+      softmax_bar();
+      const float inv = 1.0f / (l_part + x_sum[(hf ^ 1) * TILE + r]);
+      mbar_wait(o_done, (it - 1) & 1);
       tc_fence_after();
-      uint32_t sa[32], sb[32];
-      tmem_ld32(tS, sa);
-      tmem_ld32(tS + 32, sb);
+      uint32_t o[32];
+      tmem_ld32(tO, o);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(s_free);                            // both halves arrived -> S may be overwritten
-      // ---- row maximum of this half, exchanged with the partner thread ----
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      if (masked) {
+      mbar_arrive(o_free);                               // the next head's first P.V may overwrite O
+      if (q0 + r < L) {
+        __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64 + hf * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = fmaxf(m0, i < kv_valid ? __uint_as_float(sa[i]) : -INFINITY);
-          m1 = fmaxf(m1, i + 1 < kv_valid ? __uint_as_float(sa[i + 1]) : -INFINITY);
-          m2 = fmaxf(m2, 32 + i < kv_valid ? __uint_as_float(sb[i]) : -INFINITY);
-          m3 = fmaxf(m3, 33 + i < kv_valid ? __uint_as_float(sb[i + 1]) : -INFINITY);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = fmaxf(m0, __uint_as_float(sa[i]));
-          m1 = fmaxf(m1, __uint_as_float(sa[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(sb[i]));
-          m3 = fmaxf(m3, __uint_as_float(sb[i + 1]));
-        }
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(
+              pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+              pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+              pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+              pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
       }
-      float* xm = x_max + (j & 1) * 2 * TILE;
-      const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      xm[hf * TILE + r] = mine;
-      softmax_bar();
-      const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
-      bool o_waited = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const bool grow = mx > m_ref + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {          // same rows, same decision in the partner warp
-          const float m_new = grow ? mx : m_ref;
-          const float f = fast_exp2(m_ref - m_new);
-          mbar_wait(o_done, (j - 1) & 1);
-          o_waited = true;
-          tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[16];
-            tmem_ld16(tO + h * 16, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st16(tO + h * 16, o);
-          }
-          tmem_wait_st();
-          l_part *= f;
-          m_ref = m_new;
-        }
-      }
-      // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM (two 16-column stores keep the register peak low) ----
-      if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      {
-        uint32_t pk[16];
-        l_part += masked ? exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk)
-                         : exp_pack32<false>(sa, 0, kv_valid, scale_log2, m_ref, pk);
-        tmem_st16(tP, pk);
-      }
-      {
-        uint32_t pk[16];
-        l_part += masked ? exp_pack32<true>(sb, 32, kv_valid, scale_log2, m_ref, pk)
-                         : exp_pack32<false>(sb, 32, kv_valid, scale_log2, m_ref, pk);
-        tmem_st16(tP + 16, pk);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // ---- epilogue: total row sum, then O / l for this thread's 32 columns ----
-    x_sum[hf * TILE + r] = l_part;
-    softmax_bar();
-    const float inv = 1.0f / (l_part + x_sum[(hf ^ 1) * TILE + r]);
-    mbar_wait(o_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(tO, o);
-    tmem_wait_ld();
-    if (q0 + r < L) {
-      __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + head * HD64 + hf * 32;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8)
-        *reinterpret_cast<uint4*>(dst + i) = make_uint4(
-            pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-            pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-            pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-            pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
     }
   }
 
@@ -403,9 +430,18 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       ESMK_CUDA(cudaFuncSetAttribute(attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
       configured = true;
     }
-    dim3 grid(tile_capacity(T, B), H);
+    // heads per CTA: amortise the per-CTA start-up over up to 4 heads while keeping >= ~8 CTAs per SM slot
+    int hpc = 1;
+    const long tiles = (T + TILE - 1) / TILE;
+    for (int c = 4; c >= 2; --c)
+      if (tiles * ((H + c - 1) / c) >= 8L * 2 * sm_count()) { hpc = c; break; }
+    if (const char* e = getenv("ESMK_ATTN_HEADS_PER_CTA")) {   // test hook: force the head-walking depth
+      const int v = atoi(e);
+      if (v >= 1 && v <= 8) hpc = v;
+    }
+    dim3 grid(tile_capacity(T, B), (H + hpc - 1) / hpc);
     attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
-                                                      reinterpret_cast<const int4*>(tile_info), scale_log2);
+                                                      reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2);
   } else {
     dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
     attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,

@@ -165,6 +165,45 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 //               stages its own 128 rows of A and HALF of the W tile (128 rows), so W crosses L2->smem once per
 //               pair and a stage is 32 KB -> 6 stages.  The leader CTA (rank 0) issues the MMAs for both; each CTA
 //               drains its own 128 accumulator rows from its own TMEM.
+// ---- packed bf16x2 arithmetic: exactly torch's bf16 elementwise ops (operands are bf16, one RNE rounding
+// per op; products and sums of two bf16 values are exact in the hardware's internal precision) ----
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// RoPE on 64 columns held as 32 packed bf16x2 words (word i = columns 2i, 2i+1): 64/HD whole heads.
+//   lo' = bf(bf(lo*cos) - bf(hi*sin)),  hi' = bf(bf(hi*cos) + bf(lo*sin))      (esme/rotary.py:17-43)
+template <int HD>
+__device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const __nv_bfloat16* __restrict__ cos_row,
+                                              const __nv_bfloat16* __restrict__ sin_row) {
+  constexpr int HP = HD / 4;   // packed words per half head
+#pragma unroll
+  for (int i0 = 0; i0 < HP; i0 += 4) {
+    const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cos_row) + (i0 >> 2));   // cos[2 i0 .. 2 i0 + 7]
+    const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sin_row) + (i0 >> 2));
+    const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int h = 0; h < 64 / HD; ++h) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int lo = h * (HD / 2) + i0 + q, hi = lo + HP;
+        const uint32_t a = w[lo], b = w[hi];
+        w[lo] = bsub2(bmul2(a, c[q]), bmul2(b, sn[q]));
+        w[hi] = badd2(bmul2(b, c[q]), bmul2(a, sn[q]));
+      }
+    }
+  }
+}
+
 template <int EPI, int HD, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -351,6 +390,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 64; ++j)
               if (col0 + j < N) v[j] += __bfloat162float(ep.bias[col0 + j]);
+          }
+        }
+        // ---- fast path: whole 64-column group, 16-byte aligned -> packed bf16x2 math on the rounded values ----
+        if constexpr (EPI == ESMK_EPI_BIAS || EPI == ESMK_EPI_RESIDUAL || EPI == ESMK_EPI_QKV_ROPE) {
+          if (full_group && (EPI != ESMK_EPI_RESIDUAL || ep.scale == 1.0f)) {
+            uint32_t w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);   // bf(A W^T + b)
+            if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
+              if (col0 < ep.rope_cols) rope64_packed<HD>(w, cos_row, sin_row);
+            }
+            if (row_ok) {
+              if constexpr (EPI == ESMK_EPI_RESIDUAL) {                             // bf(x + y)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  w[4 * j] = badd2(rq[j].x, w[4 * j]);
+                  w[4 * j + 1] = badd2(rq[j].y, w[4 * j + 1]);
+                  w[4 * j + 2] = badd2(rq[j].z, w[4 * j + 2]);
+                  w[4 * j + 3] = badd2(rq[j].w, w[4 * j + 3]);
+                }
+              }
+              uint4* dst4 = reinterpret_cast<uint4*>(ep.C + (size_t)row * ep.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            }
+            continue;
           }
         }
         if constexpr (EPI != ESMK_EPI_BIAS) {   // (plain bias: the store's rounding is that rounding point)
