@@ -25,6 +25,8 @@
 // scores, un-normalised P rounded to bf16 before P.V, fp32 row sums of the un-rounded P, one final rounding.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "esmk_internal.h"
 
@@ -68,20 +70,30 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int col0, i
   return s0 + s1;
 }
 
+// optional latency trace (ESMK_ATTN_TRACE=<file>): clock64 stamps of one softmax thread and the MMA thread of
+// the first CTAs; nullptr in normal operation
+#define TRACE_STAMP(slot)                                                        \
+  do {                                                                           \
+    if (trace != nullptr && tr_on && tr_n < 64) tr_base[(tr_n) * 8 + (slot)] = clock64(); \
+  } while (0)
+
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-              const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2) {
+              const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
+              long long* __restrict__ trace, long long* __restrict__ cta_trace) {
+  const long long t_entry = cta_trace ? (long long)global_timer_ns() : 0;
   // work item: {first packed row of the sequence, sequence length, first query row of this tile, -}
-  const int4 info = __ldg(tile_info + blockIdx.x);
+  // grid = (head groups, tiles): launch order walks all head groups of the longest sequences first (global LPT)
+  const int4 info = __ldg(tile_info + blockIdx.y);
   const int seq_start = info.x, L = info.y, q0 = info.z;
   if (L <= 0) return;                      // unused slot of the (upper-bound sized) work list
   const int n_kv = (L + TILE - 1) / TILE;
   // this CTA walks `nh` consecutive heads of the same query tile: the producer and the MMA warp run ahead
   // into the next head while the softmax warps finish the current one, hiding the Q/K load and first-S latency
-  const int head0 = blockIdx.y * heads_per_cta;
+  const int head0 = blockIdx.x * heads_per_cta;
   const int nh = min(heads_per_cta, H - head0);
 
   extern __shared__ uint8_t smem_raw[];
@@ -138,6 +150,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_P = tmem_base + 128;
   const uint32_t tmem_O = tmem_base + 192;
+  const long long t_loop = cta_trace ? (long long)global_timer_ns() : 0;
 
   // `it` counts key blocks across all heads of this CTA: K/V stage = it & 1, stage phase = (it >> 1) & 1,
   // and the per-block barriers (s_full, s_free, p_full, o_done) complete once per block -> parity it & 1.
@@ -181,6 +194,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         umma_commit(&k_empty[st]);
       };
       int it = 0;
+      const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0);
+      long long* tr_base = trace ? trace + ((size_t)blockIdx.y * 2 + 1) * 64 * 8 : nullptr;
+      int tr_n = 0;
       for (int hi = 0; hi < nh; ++hi) {
         const int qs = hi & 1;
         mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
@@ -190,13 +206,19 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int j = 0; j < n_kv; ++j) {
           const int cur = it + j;
           const int st = cur & 1;
+          tr_n = cur;
+          TRACE_STAMP(0);
           if (j + 1 < n_kv) {
             mbar_wait_backoff(s_free, cur & 1);                          // S_j has been copied to registers
+            TRACE_STAMP(1);
             issue_s(qs, cur + 1);
+            TRACE_STAMP(2);
             if (j + 2 == n_kv) umma_commit(&q_empty[qs]);                // last S of this head: Q slot reusable
           }
           mbar_wait_backoff(p_full, cur & 1);
+          TRACE_STAMP(3);
           mbar_wait_backoff(&v_full[st], (cur >> 1) & 1);
+          TRACE_STAMP(4);
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
           const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
@@ -205,6 +227,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
           umma_commit(o_done);
           umma_commit(&v_empty[st]);
+          TRACE_STAMP(5);
         }
         it += n_kv;
       }
@@ -219,18 +242,25 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tP = tmem_P + lane_off + hf * 32;
     const uint32_t tO = tmem_O + lane_off + hf * 32;
     int it = 0;
+    const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == 64);
+    long long* tr_base = trace ? trace + (size_t)blockIdx.y * 2 * 64 * 8 : nullptr;
+    int tr_n = 0;
     for (int hi = 0; hi < nh; ++hi) {
       float m_ref = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_kv; ++j) {
         const int cur = it + j;
         const int kv_valid = L - j * TILE - hf * 64;   // valid keys among this thread's 64 columns
         const bool masked = kv_valid < 64;
+        tr_n = cur;
+        TRACE_STAMP(0);
         mbar_wait(s_full, cur & 1);
         tc_fence_after();
+        TRACE_STAMP(1);
         uint32_t sa[32], sb[32];
         tmem_ld32(tS, sa);
         tmem_ld32(tS + 32, sb);
         tmem_wait_ld();
+        TRACE_STAMP(2);
         tc_fence_before();
         mbar_arrive(s_free);                            // both halves arrived -> S may be overwritten
         // ---- row maximum of this half, exchanged with the partner thread ----
@@ -256,6 +286,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         xm[hf * TILE + r] = mine;
         softmax_bar();
+        TRACE_STAMP(3);
         const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
         bool o_waited = false;
         if (j == 0) {
@@ -283,10 +314,12 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         }
         // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM (two 16-column stores keep the register peak low) ----
+        TRACE_STAMP(4);
         if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
           mbar_wait(o_done, (cur - 1) & 1);             // (j == 0: the previous head's epilogue already waited)
           tc_fence_after();
         }
+        TRACE_STAMP(5);
         {
           uint32_t pk[16];
           l_part += masked ? exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk)
@@ -300,6 +333,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st16(tP + 16, pk);
         }
         tmem_wait_st();
+        TRACE_STAMP(6);
         tc_fence_before();
         mbar_arrive(p_full);
       }
@@ -333,6 +367,15 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+  if (cta_trace != nullptr && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long* p = cta_trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
+    p[0] = t_entry;
+    p[1] = t_loop;
+    p[2] = (long long)global_timer_ns();
+    p[3] = ((long long)smid << 32) | (long long)(n_kv * nh);
   }
 }
 
@@ -439,9 +482,55 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       const int v = atoi(e);
       if (v >= 1 && v <= 8) hpc = v;
     }
-    dim3 grid(tile_capacity(T, B), (H + hpc - 1) / hpc);
+    ESMK_REQUIRE(tile_capacity(T, B) <= 65535, "too many attention tiles for one launch (T/128 + B > 65535)");
+    dim3 grid((H + hpc - 1) / hpc, tile_capacity(T, B));
+    long long* cta_trace = nullptr;
+    const char* cta_trace_path = getenv("ESMK_ATTN_CTA_TRACE");
+    const size_t cta_n = (size_t)grid.x * grid.y * 4;
+    if (cta_trace_path != nullptr) {
+      ESMK_CUDA(cudaMalloc(&cta_trace, cta_n * sizeof(long long)));
+      ESMK_CUDA(cudaMemsetAsync(cta_trace, 0, cta_n * sizeof(long long), st));
+    }
+    long long* trace = nullptr;
+    const char* trace_path = getenv("ESMK_ATTN_TRACE");
+    const size_t trace_n = 16 * 2 * 64 * 8;
+    if (trace_path != nullptr) {
+      ESMK_CUDA(cudaMalloc(&trace, trace_n * sizeof(long long)));
+      ESMK_CUDA(cudaMemsetAsync(trace, 0, trace_n * sizeof(long long), st));
+    }
     attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
-                                                      reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2);
+                                                      reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2,
+                                                      trace, cta_trace);
+    if (cta_trace != nullptr) {   // debugging aid only
+      std::vector<long long> host(cta_n);
+      ESMK_CUDA(cudaStreamSynchronize(st));
+      ESMK_CUDA(cudaMemcpy(host.data(), cta_trace, cta_n * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(cta_trace);
+      if (FILE* f = fopen(cta_trace_path, "w")) {
+        for (size_t c = 0; c < cta_n / 4; ++c)
+          if (host[c * 4 + 2] != 0)
+            fprintf(f, "%zu %lld %lld %lld %lld %lld\n", c, host[c * 4], host[c * 4 + 1], host[c * 4 + 2],
+                    host[c * 4 + 3] >> 32, host[c * 4 + 3] & 0xffffffff);
+        fclose(f);
+      }
+    }
+    if (trace != nullptr) {   // debugging aid only: synchronous dump of the stamps
+      std::vector<long long> host(trace_n);
+      ESMK_CUDA(cudaStreamSynchronize(st));
+      ESMK_CUDA(cudaMemcpy(host.data(), trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(trace);
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (size_t c = 0; c < 16 * 2; ++c)
+          for (size_t b = 0; b < 64; ++b) {
+            const long long* p = &host[(c * 64 + b) * 8];
+            if (p[0] == 0 && p[3] == 0) continue;
+            fprintf(f, "%zu %zu %zu", c / 2, c % 2, b);
+            for (int k = 0; k < 8; ++k) fprintf(f, " %lld", p[k]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
+    }
   } else {
     dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
     attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
