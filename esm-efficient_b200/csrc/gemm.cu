@@ -168,15 +168,15 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 // ---- packed bf16x2 arithmetic: exactly torch's bf16 elementwise ops (operands are bf16, one RNE rounding
 // per op; products and sums of two bf16 values are exact in the hardware's internal precision) ----
 __device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  __nv_bfloat162 r = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  __nv_bfloat162 r = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  __nv_bfloat162 r = __hsub2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
