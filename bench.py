@@ -216,8 +216,11 @@ def main():
     local_buf = torch.zeros(t_max, V, dtype=torch.bfloat16, device=dev) if world > 1 else None
     out_pin = torch.empty((world * t_max if world > 1 else T_local, V), dtype=torch.bfloat16).pin_memory()
 
+    # BASELINE config 3 (ESMC) is quoted on predict_log_prob; the ESM2 configs on forward (logits)
+    forward = model.predict_log_prob if family == 'esmc' else model.__call__
+
     def step(tokens, cu):
-        logits = model(tokens, (cu, max_len))
+        logits = forward(tokens, (cu, max_len))
         if world > 1:                       # the single collective of the path: all-gather of logits
             local_buf[:T_local] = logits
             dist.all_gather_into_tensor(gather_buf, local_buf)
@@ -317,7 +320,7 @@ def main():
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {
-            'workload': f'{args.model} forward (tokens -> logits), packed batch <= {args.tokens} tokens per GPU, '
+            'workload': f'{args.model} {"predict_log_prob" if family == "esmc" else "forward (tokens -> logits)"}, packed batch <= {args.tokens} tokens per GPU, '
                         f'{"log-uniform 128-2048" if family == "esmc" else "lognormal(400, 0.75) clipped 30-3500"} '
                         f'residue lengths, seeded synthetic bf16 weights',
             'tokens_global': T_global, 'tokens_this_rank': T_local, 'sequences_global': len(wl['lens']),

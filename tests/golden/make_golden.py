@@ -36,6 +36,12 @@ acc = types.ModuleType('accelerate')
 acc.init_empty_weights = contextlib.nullcontext
 acc.load_checkpoint_and_dispatch = None
 sys.modules['accelerate'] = acc
+tm = types.ModuleType('torchmetrics')                       # esme/variant.py:5 imports it at module level
+tmt = types.ModuleType('torchmetrics.text')
+tmt.Perplexity = object
+tm.text = tmt
+sys.modules['torchmetrics'] = tm
+sys.modules['torchmetrics.text'] = tmt
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
@@ -167,6 +173,18 @@ def main():
     np.savez_compressed(f'{HERE}/rope.npz', q=q.numpy(), k=k.numpy(), cu_lens=cu.numpy(), max_len=np.int64(180),
                         q_rot=q_r.numpy(), k_rot=k_r.numpy(), q_rot_bf16=f32(qb), k_rot_bf16=f32(kb),
                         cos_bf16=f32(rot._cos_cached), sin_bf16=f32(rot._sin_cached))
+
+    # ---- masked-marginal variant scores (esme/variant.py:110-165), 8M model, short + windowed ------
+    from esme.variant import predict_mask_margin as ref_pmm, MaskMarginDataset as RefDS
+    model8 = build(ESM2, f'{HERE}/esm2_8m.safetensors')
+    vs = {}
+    for name, seq, ml in (('short', 'MPEAAPPVAPAPAAPTW', None), ('windowed', fa[9], 40)):
+        df = ref_pmm(model8, seq, batch_size=8, max_len=ml)
+        vs[name] = dict(seq=seq, max_len=ml, variants=list(df.index), scores=[float(x) for x in df['score']])
+    ds = RefDS(fa[9], max_len=40)
+    vs['windows'] = [[int(ds[i]['local_pos']), int(ds[i]['pos']), int(ds[i]['wt_token']),
+                      ds[i]['token'].tolist()] for i in (0, 1, 19, 20, 21, 40, len(fa[9]) - 1)]
+    json.dump(vs, open(f'{HERE}/mask_margin_8m.json', 'w'))
 
     # ---- tokenizer known answers -------------------------------------------
     p53 = ('MEEPQSDPSVEPPLSQETFSDLWKLLPENNVLSPLPSQAMDDLMLSPDDIEQWFTEDPGPDEAPRMPEAAPPVAPAPAAPTPAAPAPAPSWPLSSSVPSQKTYQGSYGFRLGFLHSGTAKSVTCTYSPALNKMFCQLAKTCPVQLWVDSTPPPGTRVRAMAIYKQSQHMTEVVRRCPHHERCSDSDGLAPPQHLIRVEGNLRVEYLDDRNTFRHSVVVPYEPPEVGSDCTTIHYNYMCNSSCMGGMNRRPILTIITLEDSSGNLLGRNSFEVRVCACPGRDRRTEEENLRKKGEPHHELPPGSTKRALPNNTSSSPQPKKKPLDGEYFTLQIRGRERFEMFRELNEALELKDAQAGKEPGGSRAHSSHLKSKKGQSTSRHKKLMFKTEGPDSD')
