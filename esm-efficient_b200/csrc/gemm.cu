@@ -182,24 +182,19 @@ __device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) {
 
 // RoPE on 64 columns held as 32 packed bf16x2 words (word i = columns 2i, 2i+1): 64/HD whole heads.
 //   lo' = bf(bf(lo*cos) - bf(hi*sin)),  hi' = bf(bf(hi*cos) + bf(lo*sin))      (esme/rotary.py:17-43)
+// cs / sn: this token's first HD/2 cos / sin values as HD/4 packed words (prefetched once per tile).
 template <int HD>
-__device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const __nv_bfloat16* __restrict__ cos_row,
-                                              const __nv_bfloat16* __restrict__ sin_row) {
+__device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const uint32_t (&cs)[HD / 4],
+                                              const uint32_t (&sn)[HD / 4]) {
   constexpr int HP = HD / 4;   // packed words per half head
 #pragma unroll
-  for (int i0 = 0; i0 < HP; i0 += 4) {
-    const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cos_row) + (i0 >> 2));   // cos[2 i0 .. 2 i0 + 7]
-    const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sin_row) + (i0 >> 2));
-    const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+  for (int h = 0; h < 64 / HD; ++h) {
 #pragma unroll
-    for (int h = 0; h < 64 / HD; ++h) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int lo = h * (HD / 2) + i0 + q, hi = lo + HP;
-        const uint32_t a = w[lo], b = w[hi];
-        w[lo] = bsub2(bmul2(a, c[q]), bmul2(b, sn[q]));
-        w[hi] = badd2(bmul2(b, c[q]), bmul2(a, sn[q]));
-      }
+    for (int i = 0; i < HP; ++i) {
+      const int lo = h * (HD / 2) + i, hi = lo + HP;
+      const uint32_t a = w[lo], b = w[hi];
+      w[lo] = bsub2(bmul2(a, cs[i]), bmul2(b, sn[i]));
+      w[hi] = badd2(bmul2(b, cs[i]), bmul2(a, sn[i]));
     }
   }
 }
@@ -336,6 +331,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         sin_row = ep.sinb + (size_t)p * HD;
       }
 
+      // ---- operands of the fused epilogue are fetched BEFORE waiting for the accumulator, so their
+      //      L2 latency hides behind the MMAs of this tile ----
+      constexpr int CSW = (EPI == ESMK_EPI_QKV_ROPE) ? HD / 4 : 1;
+      uint32_t cs[CSW], sn[CSW];
+      if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
+        if (n0 < ep.rope_cols) {
+#pragma unroll
+          for (int i = 0; i < HD / 16; ++i) {
+            const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(cos_row) + i);
+            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(sin_row) + i);
+            cs[4 * i] = c4.x; cs[4 * i + 1] = c4.y; cs[4 * i + 2] = c4.z; cs[4 * i + 3] = c4.w;
+            sn[4 * i] = s4.x; sn[4 * i + 1] = s4.y; sn[4 * i + 2] = s4.z; sn[4 * i + 3] = s4.w;
+          }
+        }
+      }
+      // bias of this warp's 128 columns, 4 values (two packed words) per lane; handed out by shuffles below
+      const bool lane_bias = ep.vec_ok && ep.bias != nullptr && (n0 + 128 <= N);
+      uint2 bias_l = make_uint2(0u, 0u);
+      if (lane_bias) bias_l = __ldg(reinterpret_cast<const uint2*>(ep.bias + n0) + lane);
+      uint4 rq0[(EPI == ESMK_EPI_RESIDUAL) ? 8 : 1];
+      if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+        if (ep.vec_ok && n0 + 64 <= N && row_ok) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(ep.R + (size_t)row * ep.ldr + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rq0[j] = r4[j];
+        }
+      }
+
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * 128;
@@ -348,7 +371,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint4 rq[(EPI == ESMK_EPI_RESIDUAL) ? 8 : 1];
         if (full_group) {
           if constexpr (EPI == ESMK_EPI_RESIDUAL) {
-            if (row_ok) {
+            if (g == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rq[j] = rq0[j];
+            } else if (row_ok) {
               const uint4* r4 = reinterpret_cast<const uint4*>(ep.R + (size_t)row * ep.ldr + col0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) rq[j] = r4[j];
@@ -376,7 +402,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (col0 >= N) continue;
 
         // ---- bias: bf(A W^T + b) is the first rounding point of every epilogue ----
-        if (ep.bias != nullptr) {
+        if (lane_bias) {
+          // columns col0 + 2p, col0 + 2p + 1 live in lane (g*32 + p) / 2, word (g*32 + p) & 1
+#pragma unroll
+          for (int p = 0; p < 32; ++p) {
+            const uint32_t b2 = __shfl_sync(0xffffffffu, (p & 1) ? bias_l.y : bias_l.x, g * 16 + (p >> 1));
+            v[2 * p] += bf16_lo(b2);
+            v[2 * p + 1] += bf16_hi(b2);
+          }
+        } else if (ep.bias != nullptr) {
           if (full_group) {
             const uint4* b4 = reinterpret_cast<const uint4*>(ep.bias + col0);   // L1-resident, branch-free
 #pragma unroll
@@ -399,7 +433,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);   // bf(A W^T + b)
             if constexpr (EPI == ESMK_EPI_QKV_ROPE) {
-              if (col0 < ep.rope_cols) rope64_packed<HD>(w, cos_row, sin_row);
+              if (col0 < ep.rope_cols) rope64_packed<HD>(w, cs, sn);
             }
             if (row_ok) {
               if constexpr (EPI == ESMK_EPI_RESIDUAL) {                             // bf(x + y)
