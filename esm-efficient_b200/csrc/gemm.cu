@@ -347,7 +347,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       // bias of this warp's 128 columns, 4 values (two packed words) per lane; handed out by shuffles below
-      const bool lane_bias = ep.vec_ok && ep.bias != nullptr && (n0 + 128 <= N);
+      // (the GELU epilogue is issue-bound, not latency-bound: it keeps plain vector loads, issued ahead of the TMEM read)
+      const bool lane_bias = (EPI != ESMK_EPI_BIAS_GELU) && ep.vec_ok && ep.bias != nullptr && (n0 + 128 <= N);
       uint2 bias_l = make_uint2(0u, 0u);
       if (lane_bias) bias_l = __ldg(reinterpret_cast<const uint2*>(ep.bias + n0) + lane);
       uint4 rq0[(EPI == ESMK_EPI_RESIDUAL) ? 8 : 1];
@@ -379,6 +380,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 8; ++j) rq[j] = r4[j];
             }
+          }
+        }
+        uint4 bq[(EPI == ESMK_EPI_BIAS_GELU) ? 8 : 1];
+        if constexpr (EPI == ESMK_EPI_BIAS_GELU) {
+          if (full_group && ep.bias != nullptr) {
+            const uint4* b4 = reinterpret_cast<const uint4*>(ep.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
           }
         }
         float v[64];
@@ -416,7 +425,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float b[8];
-              unpack_u4(__ldg(b4 + j), b);
+              if constexpr (EPI == ESMK_EPI_BIAS_GELU) unpack_u4(bq[j], b);
+              else unpack_u4(__ldg(b4 + j), b);
 #pragma unroll
               for (int q = 0; q < 8; ++q) v[8 * j + q] += b[q];
             }
