@@ -72,12 +72,19 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int col0, i
 
 // optional latency trace (ESMK_ATTN_TRACE=<file>): clock64 stamps of one softmax thread and the MMA thread of
 // the first CTAs; nullptr in normal operation
+#ifdef ESMK_ATTN_TRACING   // build with -DESMK_ATTN_TRACING to enable the latency traces (debug builds only)
 #define TRACE_STAMP(slot)                                                        \
   do {                                                                           \
     if (trace != nullptr && tr_on && tr_n < 64) tr_base[(tr_n) * 8 + (slot)] = clock64(); \
   } while (0)
+#else
+#define TRACE_STAMP(slot) \
+  do {                    \
+  } while (0)
+#endif
 
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two threads of a row live in warps w and w + 4 (same TMEM lane quadrant): only those 64 threads meet
+__device__ __forceinline__ void pair_bar(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory"); }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -194,9 +201,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         umma_commit(&k_empty[st]);
       };
       int it = 0;
-      const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0);
-      long long* tr_base = trace ? trace + ((size_t)blockIdx.y * 2 + 1) * 64 * 8 : nullptr;
-      int tr_n = 0;
+      [[maybe_unused]] const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0);
+      [[maybe_unused]] long long* tr_base = trace ? trace + ((size_t)blockIdx.y * 2 + 1) * 64 * 8 : nullptr;
+      [[maybe_unused]] int tr_n = 0;
       for (int hi = 0; hi < nh; ++hi) {
         const int qs = hi & 1;
         mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
@@ -242,9 +249,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tP = tmem_P + lane_off + hf * 32;
     const uint32_t tO = tmem_O + lane_off + hf * 32;
     int it = 0;
-    const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == 64);
-    long long* tr_base = trace ? trace + (size_t)blockIdx.y * 2 * 64 * 8 : nullptr;
-    int tr_n = 0;
+    [[maybe_unused]] const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == 64);
+    [[maybe_unused]] long long* tr_base = trace ? trace + (size_t)blockIdx.y * 2 * 64 * 8 : nullptr;
+    [[maybe_unused]] int tr_n = 0;
     for (int hi = 0; hi < nh; ++hi) {
       float m_ref = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_kv; ++j) {
@@ -285,7 +292,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         float* xm = x_max + (cur & 1) * 2 * TILE;
         const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         xm[hf * TILE + r] = mine;
-        softmax_bar();
+        pair_bar(quad);
         TRACE_STAMP(3);
         const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
         bool o_waited = false;
@@ -340,7 +347,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       it += n_kv;
       // ---- head epilogue: total row sum, then O / l for this thread's 32 columns ----
       x_sum[hf * TILE + r] = l_part;
-      softmax_bar();
+      pair_bar(quad);
       const float inv = 1.0f / (l_part + x_sum[(hf ^ 1) * TILE + r]);
       mbar_wait(o_done, (it - 1) & 1);
       tc_fence_after();
