@@ -151,6 +151,41 @@ def run_cpu_reference(args, wl, W, steps, warmup, target_seconds=4.0):
                        f'oracle/esm_oracle.py bf16-faithful mode, torch CPU fp32 GEMMs on {cores} threads'), sec
 
 
+def bench_mask_margin(args, family, layers, D, H):
+    """BASELINE config 5 (bf16 part): masked-marginal sweep of one 1,024-residue protein, batch 32 ->
+    32 forwards of 32 x 1,026 tokens; residues/s = 1024 * 1026 / sweep time (single GPU)."""
+    import torch
+    import esme
+    from esme import _lib, synthetic
+    from esme.alphabet import Alphabet
+    from esme.variant import predict_mask_margin
+    assert torch.cuda.is_available()
+    dev = torch.device('cuda', 0)
+    cls = esme.ESMC if family == 'esmc' else esme.ESM2
+    model = cls(layers, D, H)
+    model.load_state_dict(synthetic.synthetic_state_dict(family, layers, D, seed=1), strict=True)
+    model = model.to(dev).eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(6)
+    seq = ''.join(Alphabet.amino_acids[int(i)] for i in torch.randint(0, 20, (1024,), generator=g))
+    for _ in range(max(1, args.warmup // 3)):
+        predict_mask_margin(model, seq, batch_size=32)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        df = predict_mask_margin(model, seq, batch_size=32)        # ends with the single D2H of the scores
+    sec = (time.perf_counter() - t0) / args.steps
+    print(json.dumps({
+        'metric': 'residues_per_sec_mask_margin_sweep', 'value': 1024 * 1026 / sec, 'unit': UNIT, 'n_gpus': 1,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'{args.model} predict_mask_margin, one 1,024-residue protein (seed 6), batch_size 32: '
+                               f'32 packed forwards of 32 x 1,026 tokens, LM head on the 1,024 masked rows only, '
+                               f'one D2H of the [1024, 20] score matrix; wall-clock incl. host-side DataFrame',
+                   'rows': int(df.shape[0])},
+        'gpu_launches': _lib.launch_count() - launches0}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -160,6 +195,8 @@ def main():
     ap.add_argument('--model', default='esm2_650m', choices=sorted(MODELS))
     ap.add_argument('--tokens', type=int, default=50000, help='token budget per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='forward', choices=['forward', 'mask_margin'],
+                    help="'mask_margin' = BASELINE config 5: predict_mask_margin sweep over one 1,024-residue protein")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -188,6 +225,9 @@ def main():
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}))
         return
+
+    if args.workload == 'mask_margin':
+        return bench_mask_margin(args, family, layers, D, H)
 
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist

@@ -133,7 +133,8 @@ def main():
     np.savez_compressed(f'{HERE}/esm2_8m_cfg1.npz', **d)
 
     # ---- ragged: test.fa (16 proteins) + a masked/unknown/padded case --------
-    fa = [l.strip() for l in open(f'{HERE}/test.fa') if not l.startswith('>')]
+    fa = [''.join(rec.split('\n')[1:]) for rec in open(f'{HERE}/test.fa').read().split('>') if rec.strip()]
+    assert [len(x) for x in fa] == [256, 320, 458, 156, 438, 60, 217, 204, 352, 75, 128, 447, 347, 948, 85, 137]
     tokens, indices, cu, max_len = tokenize_unpad(fa)
     d = run_packed(model, tokens, cu, max_len)
     d['indices'] = indices.numpy()
