@@ -48,6 +48,9 @@ int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_dim, cons
                       const void* cosb, const void* sinb, const int32_t* pos, esmk_stream_t s) {
   GUARD(esmk::qk_norm_rope(q, k, ld, T, H, head_dim, lnq, lnk, cosb, sinb, pos, ST(s)));
 }
+int esmk_mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo, esmk_stream_t s) {
+  GUARD(esmk::mean_pool(x, ldx, cu_lens, B, D, out, ldo, ST(s)));
+}
 int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t s) {
   GUARD(esmk::softmax(logits, ld_in, out, ld_out, T, V, log, ST(s)));
 }

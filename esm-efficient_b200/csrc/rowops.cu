@@ -349,6 +349,51 @@ int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq
 }
 
 // ---------------------------------------------------------------------------
+// per-sequence mean pooling of packed rows (esme/pooling.py:44-69 `partition_mean_pool`): one CTA per
+// (sequence, 256-column slab); rows strided over the 8 warps, fp32 accumulation, one rounding at the end.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowWarps * 32)
+mean_pool_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const int32_t* __restrict__ cu, int D,
+                 __nv_bfloat16* __restrict__ out, int ldo) {
+  __shared__ float part[kRowWarps][32][8];
+  const int s = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.y * 256 + lane * 8;
+  const int r0 = cu[s], r1 = cu[s + 1];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < D) {
+    for (int r = r0 + w; r < r1; r += kRowWarps) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + (size_t)r * ldx + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[w][lane][j] = acc[j];
+  __syncthreads();
+  if (w == 0 && col < D) {
+    float tot[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRowWarps; ++k) t += part[k][lane][j];
+      tot[j] = t / (float)(r1 - r0);       // empty sequence -> NaN, as 0/0 in the reference
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)s * ldo + col) = pack8(tot);
+  }
+}
+
+int mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo, cudaStream_t st) {
+  ESMK_REQUIRE(B >= 1 && D >= 8 && D % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "mean_pool: D and pitches must be multiples of 8");
+  dim3 grid(B, (D + 255) / 256);
+  mean_pool_kernel<<<grid, kRowWarps * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, cu_lens, D, (__nv_bfloat16*)out, ldo);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // (log-)softmax over a short last dim (V <= 128): one warp per row
 // ---------------------------------------------------------------------------
 __global__ void softmax_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,

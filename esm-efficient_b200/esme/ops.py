@@ -97,6 +97,18 @@ def qk_norm_rope_(q: torch.Tensor, k: torch.Tensor, H: int, head_dim: int,
     return q, k
 
 
+def mean_pool(x: torch.Tensor, cu_lens: torch.Tensor) -> torch.Tensor:
+    """[T, D] packed rows + cu_lens int32[B+1] -> [B, D] per-sequence means (esme/pooling.py:44)."""
+    _need_cuda(x, cu_lens)
+    assert x.dtype == bf16 and x.ndim == 2 and x.stride(1) == 1
+    B, D = cu_lens.numel() - 1, x.shape[1]
+    cu = cu_lens.to(torch.int32).contiguous()
+    out = torch.empty(B, D, dtype=bf16, device=x.device)
+    L.check(L.lib.esmk_mean_pool(x.data_ptr(), x.stride(0), cu.data_ptr(), B, D, out.data_ptr(), D, _stream()),
+            'esmk_mean_pool')
+    return out
+
+
 def softmax(logits: torch.Tensor, log: bool) -> torch.Tensor:
     _need_cuda(logits)
     assert logits.dtype == bf16

@@ -76,6 +76,11 @@ ESMK_API int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_
                       const void* ln_k_weight, const void* cos, const void* sin, const int32_t* pos,
                       esmk_stream_t stream);
 
+/* esme/pooling.py:44-69 `partition_mean_pool`: out[s] = mean of the packed rows of sequence s
+ * (all tokens incl. <cls>/<eos>, as the reference), fp32 accumulation, bf16 out [B, D]. */
+ESMK_API int esmk_mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo,
+                            esmk_stream_t stream);
+
 /* esme/esm.py:297,317: (log_)softmax over the last dim of bf16 logits [T,V], bf16 out. */
 ESMK_API int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t stream);
 
