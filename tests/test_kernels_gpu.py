@@ -83,3 +83,21 @@ def test_attention_kernels_agree_and_are_batch_invariant():
     q1, k1, v1 = (sub[:, i * H * hd:(i + 1) * H * hd].unflatten(1, (H, hd)) for i in range(3))
     alone = ops.attn_varlen(q1, k1, v1, torch.tensor([0, 131], dtype=torch.int32, device=dev), 131, impl=0)
     assert torch.equal(alone, a[200:331])
+
+
+def test_partition_mean_pool():
+    """esme.pooling.partition_mean_pool vs an fp32 mean of the same bf16 rows (reference: esme/pooling.py:44-69)."""
+    from esme.pooling import PartitionMeanPool, partition_mean_pool
+    g = torch.Generator().manual_seed(3)
+    lens = [3, 1, 700, 2, 129]
+    x = torch.randn(sum(lens), 1280, generator=g).bfloat16()
+    cu = torch.tensor([0, 3, 4, 704, 706, 835], dtype=torch.int32)
+    want = torch.stack([x[a:b].float().mean(0) for a, b in zip(cu[:-1].tolist(), cu[1:].tolist())]).bfloat16()
+    got = partition_mean_pool(x.cuda(), cu.cuda())
+    assert got.shape == (5, 1280) and got.dtype == torch.bfloat16
+    assert (got.float().cpu() - want.float()).abs().max() <= 2e-3 and (got.cpu() != want).float().mean() < 0.02
+    assert torch.equal(PartitionMeanPool()(x.cuda(), cu.cuda()), got)
+    assert PartitionMeanPool._indices(cu).tolist() == sum(([i] * l for i, l in enumerate(lens)), [])
+    x320 = torch.randn(10, 320, generator=g).bfloat16()
+    got = partition_mean_pool(x320.cuda(), torch.tensor([0, 4, 10], dtype=torch.int32).cuda())
+    assert (got.float().cpu()[1] - x320[4:].float().mean(0)).abs().max() <= 4e-3
