@@ -23,8 +23,14 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_STAGE = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE = BN * BK * 2;  // 32 KB
-constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quadrant, each owning 128 of the 256 columns
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+// Epilogue warps per CTA.  The bias / GELU / residual epilogues are bound by the latency of their global
+// loads, not by issue slots: they run 16 warps (four per TMEM lane quadrant, 64 columns each, 32-column
+// register chunks, <= 112 registers).  RoPE and SwiGLU need 64 accumulator columns in registers at once and
+// keep 8 warps (two per quadrant, 128 columns each).
+__host__ __device__ constexpr int epi_warps(int epi) {
+  return (epi == ESMK_EPI_QKV_ROPE || epi == ESMK_EPI_SWIGLU) ? 8 : 16;
+}
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + epi_warps(epi) * 32; }
 constexpr int STAGES_PAIR = 6;         // 2-CTA mode: 16 KB A + 16 KB half-W per stage
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
 static_assert(STAGES_PAIR * (A_STAGE + B_STAGE / 2) == STAGES * (A_STAGE + B_STAGE), "same smem footprint");
@@ -200,9 +206,10 @@ __device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const uint32_t 
 }
 
 template <int EPI, int HD, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
             EpiParams ep) {
+  constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
   constexpr int BSTAGE = PAIR ? B_STAGE / 2 : B_STAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -309,8 +316,140 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (PAIR) umma_commit_pair(&acc_full[as]); else umma_commit(&acc_full[as]);
       }
     }
+  } else if constexpr (EPI_WARPS == 16) {
+    // ===================== epilogue, 16 warps: bias / GELU / residual =====================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int cg = (warp - 2) >> 2;      // which 64-column group of the tile this warp owns
+    int it = 0;
+    for (int tile = group; tile < num_tiles; tile += n_groups, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_blocks) * TILE_M + rank * BM;
+      const int n0 = (tile % n_blocks) * BN + cg * 64;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const bool full = ep.vec_ok && (n0 + 64 <= N);   // all 64 columns exist and 16-byte accesses are legal
+
+      // ---- operands fetched BEFORE waiting for the accumulator: their latency hides behind this tile's MMAs
+      const bool lane_bias = (EPI != ESMK_EPI_BIAS_GELU) && full && ep.bias != nullptr;
+      uint32_t bias_w = 0;                 // columns n0 + 2*lane, n0 + 2*lane + 1; handed out by shuffles
+      if (lane_bias) bias_w = __ldg(reinterpret_cast<const uint32_t*>(ep.bias + n0) + lane);
+      uint4 rq[(EPI == ESMK_EPI_RESIDUAL) ? 8 : 1];
+      if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+        if (full && row_ok) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(ep.R + (size_t)row * ep.ldr + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rq[j] = r4[j];
+        }
+      }
+      uint4 bq[(EPI == ESMK_EPI_BIAS_GELU) ? 8 : 1];
+      if constexpr (EPI == ESMK_EPI_BIAS_GELU) {
+        if (full && ep.bias != nullptr) {
+          const uint4* b4 = reinterpret_cast<const uint4*>(ep.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
+        }
+      }
+
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + cg * 64;
+
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = n0 + c * 32;
+        float v[32];
+        {
+          uint32_t r0[32];
+          tmem_ld32(t_row + c * 32, r0);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+        }
+        if (c == 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+            else mbar_arrive(&acc_empty[as]);
+          }
+        }
+        if (col0 >= N) continue;
+
+        if (full) {
+          // ---- bias: bf(A W^T + b) is the first rounding point of every epilogue ----
+          if (lane_bias) {
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const uint32_t b2 = __shfl_sync(0xffffffffu, bias_w, c * 16 + p);
+              v[2 * p] += bf16_lo(b2);
+              v[2 * p + 1] += bf16_hi(b2);
+            }
+          } else if (EPI == ESMK_EPI_BIAS_GELU && ep.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float b[8];
+              unpack_u4(bq[c * 4 + j], b);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[8 * j + q] += b[q];
+            }
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+          if constexpr (EPI == ESMK_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              w[j] = pack_bf16(gelu_fast(bf16_lo(w[j])), gelu_fast(bf16_hi(w[j])));
+          }
+          if (!row_ok) continue;
+          if constexpr (EPI == ESMK_EPI_RESIDUAL) {
+            if (ep.scale == 1.0f) {                                              // bf(x + y), packed
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r = rq[c * 4 + j];
+                w[4 * j] = badd2(r.x, w[4 * j]);
+                w[4 * j + 1] = badd2(r.y, w[4 * j + 1]);
+                w[4 * j + 2] = badd2(r.z, w[4 * j + 2]);
+                w[4 * j + 3] = badd2(r.w, w[4 * j + 3]);
+              }
+            } else {                                                             // bf(x + bf(y / s))
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r = rq[c * 4 + j];
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t y = pack_bf16(bf16_lo(w[4 * j + q]) / ep.scale, bf16_hi(w[4 * j + q]) / ep.scale);
+                  w[4 * j + q] = badd2(rw[q], y);
+                }
+              }
+            }
+          }
+          uint4* dst4 = reinterpret_cast<uint4*>(ep.C + (size_t)row * ep.ldc + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {
+          // ---- ragged right edge or unaligned operands: element-wise (compile-time indices keep v[] in registers)
+          if (!row_ok) continue;
+          __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < N) {
+              float y = v[j];
+              if (ep.bias != nullptr) y += __bfloat162float(ep.bias[col0 + j]);
+              y = bfr(y);
+              if constexpr (EPI == ESMK_EPI_BIAS_GELU) y = gelu_fast(y);
+              if constexpr (EPI == ESMK_EPI_RESIDUAL)
+                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(y / ep.scale);
+              dst[j] = __float2bfloat16_rn(y);
+            }
+          }
+        }
+      }
+    }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue, 8 warps: QKV + RoPE / SwiGLU =====================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;    // which 128-column half of the tile this warp owns
     int it = 0;
@@ -577,7 +716,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, in
   } else {
     cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
   }
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
   ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, ep));
