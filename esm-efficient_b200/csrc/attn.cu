@@ -44,30 +44,89 @@ constexpr int TILE = 128;                  // query rows per CTA == keys per blo
 constexpr int HD64 = 64;
 constexpr int Q_BYTES = TILE * HD64 * 2;   // 16 KB
 constexpr int AT_TMEM_COLS = 256;
-constexpr int AT_THREADS = 64 + 256;
-constexpr int AT_SMEM = Q_BYTES * 6 + 1024 + 192 + 2 * 2 * TILE * 4 /*row-max exchange, double-buffered*/ +
-                        2 * TILE * 4 /*row-sum exchange*/;
+constexpr int AT_THREADS = 64 + 128;         // producer warp, MMA warp, 4 softmax warps (one thread per query row)
+constexpr int AT_SMEM = Q_BYTES * 6 + 1024 + 192;
+constexpr int kDefaultPoly = 0;            // eighths of the exponentials on the FMA pipes (see exp_pack32): measured, no gain
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
-// exp2(x*c - m) for 32 fp32 values (already in registers) -> 16 packed bf16x2 words; returns the fp32
-// sum of the un-rounded values
-template <bool MASK>
-__device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int col0, int kv_valid, float scale_log2,
-                                            float m_ref, uint32_t* pk) {
-  float s0 = 0.f, s1 = 0.f;
+// Software exp2 on the FMA pipes (the MUFU unit gives only 16 ex2 per clock per SM, half of what the tensor
+// pipe could consume at head_dim 64): floor(x) falls out of one round-down add against the 1.5*2^23 magic
+// constant, the fraction goes through a degree-3 polynomial (max relative error 1e-4, below the bf16 rounding
+// of P) and the integer part is added into the exponent field.
+constexpr float kMagic = 12582912.0f;              // 1.5 * 2^23
+constexpr float kEx2C1 = 0.695146143436431884765625f;
+constexpr float kEx2C2 = 0.227564394474029541015625f;
+constexpr float kEx2C3 = 0.077119089663028717041015625f;
+
+// which of every 8 column pairs take the polynomial path (evenly spread, POLY in 0..8)
+template <int POLY>
+__device__ __forceinline__ constexpr bool poly_pair(int pr) {
+  return ((pr & 7) * POLY) / 8 != (((pr & 7) + 1) * POLY) / 8;
+}
+
+// P = exp2(s*c - m) for 32 fp32 scores held in registers -> 16 packed bf16x2 words; returns the fp32 sum of the
+// un-rounded values.  Packed f32x2 arithmetic halves the issue slots of the scale / polynomial / sum steps.
+template <int POLY, bool MASK>
+__device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int kv_valid, float c, float m, uint32_t* pk) {
+  const uint64_t c2 = f2_pack(c, c);
+  const uint64_t negm2 = f2_pack(-m, -m);
+  const uint64_t magic2 = f2_pack(kMagic, kMagic);
+  uint64_t acc0 = f2_pack(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), scale_log2, -m_ref));
-    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_ref));
-    if (MASK) {
-      p0 = (col0 + i < kv_valid) ? p0 : 0.f;
-      p1 = (col0 + i + 1 < kv_valid) ? p1 : 0.f;
+  for (int pr = 0; pr < 16; ++pr) {
+    const uint64_t sv = f2_pack(__uint_as_float(s[2 * pr]), __uint_as_float(s[2 * pr + 1]));
+    float p0, p1;
+    float x0, x1;
+    f2_unpack(f2_fma(sv, c2, negm2), x0, x1);              // x = s*c - m
+    if (poly_pair<POLY>(pr)) {
+      float n0, n1, q0, q1;
+      x0 = fminf(fmaxf(x0, -126.0f), 126.0f);                // keeps the exponent insert inside the normal range
+      x1 = fminf(fmaxf(x1, -126.0f), 126.0f);
+      const uint64_t x = f2_pack(x0, x1);
+      const uint64_t xr = f2_add_rm(x, magic2);              // magic + floor(x), exact
+      f2_unpack(xr, n0, n1);
+      const uint64_t f = f2_sub(x, f2_sub(xr, magic2));      // fraction in [0, 1)
+      uint64_t q = f2_fma(f2_pack(kEx2C3, kEx2C3), f, f2_pack(kEx2C2, kEx2C2));
+      q = f2_fma(q, f, f2_pack(kEx2C1, kEx2C1));
+      q = f2_fma(q, f, f2_pack(1.0f, 1.0f));
+      f2_unpack(q, q0, q1);
+      p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(n0) << 23));
+      p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(n1) << 23));
+    } else {
+      p0 = fast_exp2(x0);
+      p1 = fast_exp2(x1);
     }
-    s0 += p0;
-    s1 += p1;
-    pk[i >> 1] = pack_bf16(p0, p1);
+    if (MASK) {
+      p0 = (2 * pr < kv_valid) ? p0 : 0.f;
+      p1 = (2 * pr + 1 < kv_valid) ? p1 : 0.f;
+    }
+    if (pr & 1) acc1 = f2_add(acc1, f2_pack(p0, p1));
+    else acc0 = f2_add(acc0, f2_pack(p0, p1));
+    pk[pr] = pack_bf16(p0, p1);
   }
-  return s0 + s1;
+  float a0, a1;
+  f2_unpack(f2_add(acc0, acc1), a0, a1);
+  return a0 + a1;
+}
+
+// maximum of the first min(32, kv_valid) of 32 scores
+template <bool MASK>
+__device__ __forceinline__ float chunk_max(const uint32_t (&s)[32], int kv_valid) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (MASK) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      m0 = fmaxf(m0, i < kv_valid ? __uint_as_float(s[i]) : -INFINITY);
+      m1 = fmaxf(m1, i + 1 < kv_valid ? __uint_as_float(s[i + 1]) : -INFINITY);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      m0 = fmaxf(m0, __uint_as_float(s[i]));
+      m1 = fmaxf(m1, __uint_as_float(s[i + 1]));
+    }
+  }
+  return fmaxf(m0, m1);
 }
 
 // optional latency trace (ESMK_ATTN_TRACE=<file>): clock64 stamps of one softmax thread and the MMA thread of
@@ -83,9 +142,7 @@ __device__ __forceinline__ float exp_pack32(const uint32_t (&s)[32], int col0, i
   } while (0)
 #endif
 
-// the two threads of a row live in warps w and w + 4 (same TMEM lane quadrant): only those 64 threads meet
-__device__ __forceinline__ void pair_bar(int quad) { asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory"); }
-
+template <int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
@@ -121,8 +178,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* o_done = bars + 15;
   uint64_t* o_free = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-  float* x_max = reinterpret_cast<float*>(bars + 20);   // [2 parity][2 half][TILE]
-  float* x_sum = x_max + 4 * TILE;                       // [2 half][TILE]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,10 +195,10 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(p_full, 256);
+    mbar_init(s_free, 4);    // one arrival per softmax warp
+    mbar_init(p_full, 4);
     mbar_init(o_done, 1);
-    mbar_init(o_free, 256);
+    mbar_init(o_free, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -187,10 +242,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(TILE, TILE, 0, 0);   // Q K^T : both K-major from smem
       constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
-      auto issue_s = [&](int qs, int blk) {                             // S = Q[qs] . K[blk & 1]^T
+      // the last key block of a sequence is trimmed to its valid keys rounded up to 16: N of the S MMA and the
+      // number of K steps of the P.V MMA (the softmax warps skip the same columns)
+      auto issue_s = [&](int qs, int blk, int j) {                      // S = Q[qs] . K[blk & 1]^T, key block j
         const int st = blk & 1;
+        const int n_keys = min(TILE, ((L - j * TILE) + 15) & ~15);
+        const uint32_t idesc_s = make_idesc_bf16(TILE, n_keys, 0, 0);   // Q K^T : both K-major from smem
         mbar_wait_backoff(&k_full[st], (blk >> 1) & 1);
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * Q_BYTES), 16, 1024, 2);
@@ -208,7 +266,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int qs = hi & 1;
         mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
         if (it > 0) mbar_wait_backoff(s_free, (it - 1) & 1);            // previous head's last S is in registers
-        issue_s(qs, it);
+        issue_s(qs, it, 0);
         if (n_kv == 1) umma_commit(&q_empty[qs]);
         for (int j = 0; j < n_kv; ++j) {
           const int cur = it + j;
@@ -218,7 +276,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (j + 1 < n_kv) {
             mbar_wait_backoff(s_free, cur & 1);                          // S_j has been copied to registers
             TRACE_STAMP(1);
-            issue_s(qs, cur + 1);
+            issue_s(qs, cur + 1, j + 1);
             TRACE_STAMP(2);
             if (j + 2 == n_kv) umma_commit(&q_empty[qs]);                // last S of this head: Q slot reusable
           }
@@ -229,8 +287,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
           const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
-#pragma unroll
-          for (int k = 0; k < TILE / 16; ++k)   // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
+          const int k_steps = min(TILE / 16, ((L - j * TILE) + 15) >> 4);
+          for (int k = 0; k < k_steps; ++k)     // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
             umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
           umma_commit(o_done);
           umma_commit(&v_empty[st]);
@@ -240,131 +298,158 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
   } else {
-    // ===================== softmax warps: two threads per query row =====================
-    const int quad = warp & 3;                 // TMEM lane quadrant
-    const int hf = (warp - 2) >> 2;            // which 64-key half of each block / 32-column half of O
+    // ===================== softmax warps: one thread per query row =====================
+    // Every instruction that goes through the SM's MIO queue (mbarrier polls, TMEM loads/stores, shared
+    // memory) waits behind the MUFU ops of whichever CTA is in its exponential phase, so the per-block
+    // protocol is kept to the minimum: one S wait, four TMEM loads, one arrive, one O wait, four P stores,
+    // one arrive per 128 exponentials -- no cross-thread exchange of the row maximum or the row sum.
+    const int quad = warp & 3;                 // TMEM lane quadrant (warps 2,3,4,5 -> quadrants 2,3,0,1)
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_S + lane_off + hf * 64;
-    const uint32_t tP = tmem_P + lane_off + hf * 32;
-    const uint32_t tO = tmem_O + lane_off + hf * 32;
+    const uint32_t tS = tmem_S + lane_off;
+    const uint32_t tP = tmem_P + lane_off;
+    const uint32_t tO = tmem_O + lane_off;
     int it = 0;
     [[maybe_unused]] const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == 64);
     [[maybe_unused]] long long* tr_base = trace ? trace + (size_t)blockIdx.y * 2 * 64 * 8 : nullptr;
     [[maybe_unused]] int tr_n = 0;
+    // a warp whose 32 query rows all lie beyond the end of the sequence keeps the barrier protocol but skips
+    // the exponentials and the stores
+    const bool rows_ok = q0 + quad * 32 < L;
     for (int hi = 0; hi < nh; ++hi) {
-      float m_ref = -INFINITY, l_part = 0.f;
+      float m_ref = -INFINITY, l_sum = 0.f;
       for (int j = 0; j < n_kv; ++j) {
         const int cur = it + j;
-        const int kv_valid = L - j * TILE - hf * 64;   // valid keys among this thread's 64 columns
-        const bool masked = kv_valid < 64;
+        // valid keys among the block's 128 columns (none for a warp without valid rows); only the last key
+        // block of a sequence is masked, and there whole 32-column chunks without valid keys are skipped
+        const int kv_valid = rows_ok ? L - j * TILE : 0;
+        const bool masked = kv_valid < TILE;
         tr_n = cur;
         TRACE_STAMP(0);
         mbar_wait(s_full, cur & 1);
         tc_fence_after();
         TRACE_STAMP(1);
-        uint32_t sa[32], sb[32];
-        tmem_ld32(tS, sa);
-        tmem_ld32(tS + 32, sb);
+        uint32_t s0[32], s1[32], s2[32], s3[32];   // (unconditional loads: conditional asm outputs go to local memory)
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tmem_ld32(tS + 64, s2);
+        tmem_ld32(tS + 96, s3);
         tmem_wait_ld();
         TRACE_STAMP(2);
         tc_fence_before();
-        mbar_arrive(s_free);                            // both halves arrived -> S may be overwritten
-        // ---- row maximum of this half, exchanged with the partner thread ----
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            m0 = fmaxf(m0, i < kv_valid ? __uint_as_float(sa[i]) : -INFINITY);
-            m1 = fmaxf(m1, i + 1 < kv_valid ? __uint_as_float(sa[i + 1]) : -INFINITY);
-            m2 = fmaxf(m2, 32 + i < kv_valid ? __uint_as_float(sb[i]) : -INFINITY);
-            m3 = fmaxf(m3, 33 + i < kv_valid ? __uint_as_float(sb[i + 1]) : -INFINITY);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            m0 = fmaxf(m0, __uint_as_float(sa[i]));
-            m1 = fmaxf(m1, __uint_as_float(sa[i + 1]));
-            m2 = fmaxf(m2, __uint_as_float(sb[i]));
-            m3 = fmaxf(m3, __uint_as_float(sb[i + 1]));
-          }
-        }
-        float* xm = x_max + (cur & 1) * 2 * TILE;
-        const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        xm[hf * TILE + r] = mine;
-        pair_bar(quad);
-        TRACE_STAMP(3);
-        const float mx = fmaxf(mine, xm[(hf ^ 1) * TILE + r]) * scale_log2;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);             // all 4 warps arrived -> S may be overwritten
         bool o_waited = false;
-        if (j == 0) {
-          m_ref = mx;
-        } else {
-          const bool grow = mx > m_ref + kRescaleThreshold;
-          if (__any_sync(0xffffffffu, grow)) {          // same rows, same decision in the partner warp
-            const float m_new = grow ? mx : m_ref;
-            const float f = fast_exp2(m_ref - m_new);
-            mbar_wait(o_done, (cur - 1) & 1);
-            o_waited = true;
-            tc_fence_after();
+        if (rows_ok) {
+          float mine;
+          if (!masked) {
+            mine = fmaxf(fmaxf(chunk_max<false>(s0, 32), chunk_max<false>(s1, 32)),
+                         fmaxf(chunk_max<false>(s2, 32), chunk_max<false>(s3, 32)));
+          } else {
+            mine = chunk_max<true>(s0, kv_valid);
+            if (kv_valid > 32) mine = fmaxf(mine, chunk_max<true>(s1, kv_valid - 32));
+            if (kv_valid > 64) mine = fmaxf(mine, chunk_max<true>(s2, kv_valid - 64));
+            if (kv_valid > 96) mine = fmaxf(mine, chunk_max<true>(s3, kv_valid - 96));
+          }
+          TRACE_STAMP(3);
+          const float mx = mine * scale_log2;
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            // lazy rescale: P = exp2(x - m_ref) is a bf16 FLOAT, so its relative precision does not depend on
+            // m_ref; the reference moves only when a row maximum outgrows it by more than 2^kRescaleThreshold
+            const bool grow = mx > m_ref + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              const float m_new = grow ? mx : m_ref;
+              const float f = fast_exp2(m_ref - m_new);
+              mbar_wait(o_done, (cur - 1) & 1);
+              o_waited = true;
+              tc_fence_after();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t o[16];
-              tmem_ld16(tO + h * 16, o);
-              tmem_wait_ld();
+              for (int h = 0; h < 4; ++h) {
+                uint32_t o[16];
+                tmem_ld16(tO + h * 16, o);
+                tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st16(tO + h * 16, o);
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st16(tO + h * 16, o);
+              }
+              tmem_wait_st();
+              l_sum *= f;
+              m_ref = m_new;
             }
-            tmem_wait_st();
-            l_part *= f;
-            m_ref = m_new;
           }
         }
-        // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM (two 16-column stores keep the register peak low) ----
+        // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM, 32 keys (16 packed columns) per store ----
         TRACE_STAMP(4);
         if (j > 0 && !o_waited) {                       // P_{j-1} must have been consumed before it is overwritten
           mbar_wait(o_done, (cur - 1) & 1);             // (j == 0: the previous head's epilogue already waited)
           tc_fence_after();
         }
         TRACE_STAMP(5);
-        {
+        if (!masked) {
           uint32_t pk[16];
-          l_part += masked ? exp_pack32<true>(sa, 0, kv_valid, scale_log2, m_ref, pk)
-                           : exp_pack32<false>(sa, 0, kv_valid, scale_log2, m_ref, pk);
+          l_sum += exp_pack32<POLY, false>(s0, 32, scale_log2, m_ref, pk);
           tmem_st16(tP, pk);
-        }
-        {
-          uint32_t pk[16];
-          l_part += masked ? exp_pack32<true>(sb, 32, kv_valid, scale_log2, m_ref, pk)
-                           : exp_pack32<false>(sb, 32, kv_valid, scale_log2, m_ref, pk);
+          l_sum += exp_pack32<POLY, false>(s1, 32, scale_log2, m_ref, pk);
           tmem_st16(tP + 16, pk);
+          l_sum += exp_pack32<POLY, false>(s2, 32, scale_log2, m_ref, pk);
+          tmem_st16(tP + 32, pk);
+          l_sum += exp_pack32<POLY, false>(s3, 32, scale_log2, m_ref, pk);
+          tmem_st16(tP + 48, pk);
+        } else {
+          uint32_t pk[16];
+          if (kv_valid > 0) {
+            l_sum += exp_pack32<POLY, true>(s0, kv_valid, scale_log2, m_ref, pk);
+            tmem_st16(tP, pk);
+          }
+          if (kv_valid > 32) {
+            l_sum += exp_pack32<POLY, true>(s1, kv_valid - 32, scale_log2, m_ref, pk);
+            tmem_st16(tP + 16, pk);
+          }
+          if (kv_valid > 64) {
+            l_sum += exp_pack32<POLY, true>(s2, kv_valid - 64, scale_log2, m_ref, pk);
+            tmem_st16(tP + 32, pk);
+          }
+          if (kv_valid > 96) {
+            l_sum += exp_pack32<POLY, true>(s3, kv_valid - 96, scale_log2, m_ref, pk);
+            tmem_st16(tP + 48, pk);
+          }
         }
         tmem_wait_st();
         TRACE_STAMP(6);
         tc_fence_before();
-        mbar_arrive(p_full);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
       }
       it += n_kv;
-      // ---- head epilogue: total row sum, then O / l for this thread's 32 columns ----
-      x_sum[hf * TILE + r] = l_part;
-      pair_bar(quad);
-      const float inv = 1.0f / (l_part + x_sum[(hf ^ 1) * TILE + r]);
+      // ---- head epilogue: O / l for this thread's row ----
+      const float inv = 1.0f / l_sum;
       mbar_wait(o_done, (it - 1) & 1);
       tc_fence_after();
-      uint32_t o[32];
-      tmem_ld32(tO, o);
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO, o0);
+      tmem_ld32(tO + 32, o1);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(o_free);                               // the next head's first P.V may overwrite O
-      if (q0 + r < L) {
-        __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64 + hf * 32;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);                // the next head's first P.V may overwrite O
+      if (rows_ok && q0 + r < L) {
+        __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64;
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
           *reinterpret_cast<uint4*>(dst + i) = make_uint4(
-              pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+              pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
+              pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
+              pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
+              pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(dst + 32 + i) = make_uint4(
+              pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
+              pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
+              pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
+              pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
       }
     }
   }
@@ -475,10 +560,17 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
-    static bool configured = false;
-    if (!configured) {
-      ESMK_CUDA(cudaFuncSetAttribute(attn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      configured = true;
+    // share of the exponentials evaluated on the FMA pipes (eighths); ESMK_ATTN_POLY overrides (A/B measurements)
+    using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
+                              long long*, long long*);
+    static kernel_t kernel = nullptr;
+    if (kernel == nullptr) {
+      int poly = kDefaultPoly;
+      if (const char* e = getenv("ESMK_ATTN_POLY")) poly = atoi(e);
+      kernel_t k = poly <= 0 ? attn64_kernel<0> : poly == 1 ? attn64_kernel<1> : poly == 2 ? attn64_kernel<2>
+                   : poly == 3 ? attn64_kernel<3> : poly == 4 ? attn64_kernel<4> : attn64_kernel<5>;
+      ESMK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      kernel = k;
     }
     // heads per CTA: amortise the per-CTA start-up over up to 4 heads while keeping >= ~8 CTAs per SM slot
     int hpc = 1;
@@ -505,7 +597,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       ESMK_CUDA(cudaMalloc(&trace, trace_n * sizeof(long long)));
       ESMK_CUDA(cudaMemsetAsync(trace, 0, trace_n * sizeof(long long), st));
     }
-    attn64_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
+    kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
                                                       reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2,
                                                       trace, cta_trace);
     if (cta_trace != nullptr) {   // debugging aid only

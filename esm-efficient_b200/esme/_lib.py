@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libesmk.so')
+LIB_PATH = os.environ.get('ESMK_LIB_PATH') or os.path.join(_HERE, '_lib', 'libesmk.so')   # override: debug builds (tracing)
 
 
 class EsmkError(RuntimeError):

@@ -313,6 +313,62 @@ def attn_accuracy():
 
 
 @case
+def attn_probe():
+    """Where does the tcgen05 kernel's extra noise over flash-attn come from?  (a) q = 0: P = 1 exactly, so any
+    error is the P.V accumulation; (b) v = 1: output = sum(bf16 P) / sum(P), isolates the P rounding;
+    (c) the plain case, against the exact fp64 result, next to the generic kernel and flash-attn."""
+    torch, ops, L, O = _imports()
+    dev = 'cuda'
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    H, hd, lens = 4, 64, [700, 1300, 90, 257]
+    T, D = sum(lens), H * hd
+    base = torch.randn(T, 3 * D, generator=g)
+    base[:, :2 * D] *= 1.4
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    p64 = O._Prec('fp64')
+    for tag in ('plain', 'intqk', 'onehot_v'):
+        qkv = base.clone()
+        lens_t, cu_t = lens, cu
+        if tag == 'intqk':                      # integer q, k: every score is exact in any accumulator
+            qkv[:, :2 * D] = torch.randint(-2, 3, (T, 2 * D), generator=g).float()
+        if tag == 'onehot_v':                   # output column d = share of the softmax mass on keys = d mod 64
+            oh = torch.zeros(T, hd)
+            oh[torch.arange(T), torch.arange(T) % hd] = 1.0
+            qkv[:, 2 * D:] = oh.repeat(1, H)
+        if tag == 'v1':
+            qkv[:, 2 * D:] = 1.0
+        if tag == 'short':
+            lens_t = [100, 128, 60, 30] * 7
+            qkv = qkv[:sum(lens_t)]
+            cu_t = torch.zeros(len(lens_t) + 1, dtype=torch.int32)
+            cu_t[1:] = torch.cumsum(torch.tensor(lens_t), 0)
+        qkv = qkv.bfloat16()
+        Tt = qkv.shape[0]
+        q, k, v = (qkv[:, i * D:(i + 1) * D].double().reshape(Tt, H, hd) for i in range(3))
+        exact = O.varlen_attention(q, k, v, cu_t, p64).reshape(Tt, D)
+        qd = qkv.to(dev)
+        a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+        for name, impl in (('tcgen05', 0), ('generic', 1)):
+            r = _cmp(f'{tag}_{name}', ops.attn_varlen(a, b, c, cu_t.to(dev), max(lens_t), impl=impl), exact, out)
+            out[f'{tag}_{name}'] = {k_: r[k_] for k_ in ('max_abs', 'rms_rel')}
+        r = _cmp(f'{tag}_oracle_bf16', O.varlen_attention(q.float(), k.float(), v.float(), cu_t, O._Prec('bf16')).reshape(Tt, D), exact, out)
+        out[f'{tag}_oracle_bf16'] = {k_: r[k_] for k_ in ('max_abs', 'rms_rel')}
+        r = _cmp(f'{tag}_exact_rounded', exact.bfloat16(), exact, out)
+        out[f'{tag}_exact_rounded'] = {k_: r[k_] for k_ in ('max_abs', 'rms_rel')}
+        try:
+            from flash_attn import flash_attn_varlen_func
+            fa = flash_attn_varlen_func(a.contiguous(), b.contiguous(), c.contiguous(), cu_t.to(dev), cu_t.to(dev),
+                                        max(lens_t), max(lens_t))
+            r = _cmp(f'{tag}_flash', fa.reshape(Tt, D), exact, out)
+            out[f'{tag}_flash'] = {k_: r[k_] for k_ in ('max_abs', 'rms_rel')}
+        except Exception as e:
+            out['flash_attn_error'] = repr(e)[:200]
+    return out
+
+
+@case
 def perf_attn():
     torch, ops, L, O = _imports()
     dev = 'cuda'

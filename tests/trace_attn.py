@@ -20,7 +20,7 @@ torch.cuda.synchronize()
 rows = [list(map(int, l.split())) for l in open(os.environ['ESMK_ATTN_TRACE'])]
 print('records', len(rows))
 import collections
-for role, names in ((0, ['wait_s_full', 'ldtm', 'max+bar', 'rescale?+exps', 'wait_o_done', 'st_P']),
+for role, names in ((0, ['wait_s_full', 'ldtm', 'arrive+row max', 'rescale check', 'wait_o_done', 'exp+st_P']),
                     (1, ['wait_s_free', 'issue_S', 'wait_p_full', 'wait_v_full', 'issue_PV'])):
     acc = collections.defaultdict(list)
     per_block = []
