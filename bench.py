@@ -167,6 +167,14 @@ def bench_mask_margin(args, family, layers, D, H):
     model = model.to(dev).eval().requires_grad_(False)
     g = torch.Generator().manual_seed(6)
     seq = ''.join(Alphabet.amino_acids[int(i)] for i in torch.randint(0, 20, (1024,), generator=g))
+    quant_note, score_check = 'bf16 weights', None
+    if args.quant != 'none':
+        # BASELINE config 5: int4 weight-quantised FFN.  Scores of the bf16 model first, for the comparison.
+        from esme.quantization import quantize_model_
+        base = predict_mask_margin(model, seq, batch_size=32)
+        which = ('ffn',) if args.quant.endswith('ffn') else ('q', 'k', 'v', 'out', 'ffn')
+        quantize_model_(model, 4 if args.quant.startswith('4bit') else 8, which=which)
+        quant_note = f'{args.quant} weight-only quantised linears (esme/quantization.py formats), GEMMs in bf16 on the dequantised weight'
     for _ in range(max(1, args.warmup // 3)):
         predict_mask_margin(model, seq, batch_size=32)
     torch.cuda.synchronize()
@@ -175,6 +183,12 @@ def bench_mask_margin(args, family, layers, D, H):
     for _ in range(args.steps):
         df = predict_mask_margin(model, seq, batch_size=32)        # ends with the single D2H of the scores
     sec = (time.perf_counter() - t0) / args.steps
+    if args.quant != 'none':
+        a = torch.tensor(base['score'].to_numpy(), dtype=torch.float64)
+        b = torch.tensor(df['score'].to_numpy(), dtype=torch.float64)
+        ra, rb = a.argsort().argsort().double(), b.argsort().argsort().double()
+        score_check = {'spearman_vs_bf16': float(torch.corrcoef(torch.stack((ra, rb)))[0, 1]),
+                       'mean_abs_diff_vs_bf16': float((a - b).abs().mean()), 'max_abs_diff_vs_bf16': float((a - b).abs().max())}
     print(json.dumps({
         'metric': 'residues_per_sec_mask_margin_sweep', 'value': 1024 * 1026 / sec, 'unit': UNIT, 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
@@ -182,7 +196,7 @@ def bench_mask_margin(args, family, layers, D, H):
         'config': {'workload': f'{args.model} predict_mask_margin, one 1,024-residue protein (seed 6), batch_size 32: '
                                f'32 packed forwards of 32 x 1,026 tokens, LM head on the 1,024 masked rows only, '
                                f'one D2H of the [1024, 20] score matrix; wall-clock incl. host-side DataFrame',
-                   'rows': int(df.shape[0])},
+                   'rows': int(df.shape[0]), 'weights': quant_note, 'scores_vs_bf16': score_check},
         'gpu_launches': _lib.launch_count() - launches0}))
 
 
@@ -195,6 +209,8 @@ def main():
     ap.add_argument('--model', default='esm2_650m', choices=sorted(MODELS))
     ap.add_argument('--tokens', type=int, default=50000, help='token budget per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quant', default='none', choices=['none', '4bit-ffn', '4bit', '8bit-ffn', '8bit'],
+                    help='weight-only quantisation of the layer linears (mask_margin workload; BASELINE config 5 = 4bit-ffn)')
     ap.add_argument('--workload', default='forward', choices=['forward', 'mask_margin'],
                     help="'mask_margin' = BASELINE config 5: predict_mask_margin sweep over one 1,024-residue protein")
     args = ap.parse_args()

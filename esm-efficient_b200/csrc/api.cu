@@ -63,6 +63,12 @@ int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* 
                      esmk_stream_t s) {
   GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_info, B, T, H, head_dim, max_len, impl, ST(s)));
 }
+int esmk_quantize(const void* W, int N, int K, int bits, void* data, float* scale, esmk_stream_t s) {
+  GUARD(esmk::quantize(W, N, K, bits, data, scale, ST(s)));
+}
+int esmk_dequantize(const void* data, const float* scale, int N, int K, int bits, void* W, esmk_stream_t s) {
+  GUARD(esmk::dequantize(data, scale, N, K, bits, W, ST(s)));
+}
 void esmk_profile_enable(int on) { esmk::profile_enable(on); }
 int esmk_profile_read(float* ms, int* launches, int n_categories) {
   if (ms == nullptr || launches == nullptr) return esmk::fail("esmk_profile_read", "null argument");

@@ -249,7 +249,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int st = blk & 1;
         const int n_keys = min(TILE, ((L - j * TILE) + 15) & ~15);
         const uint32_t idesc_s = make_idesc_bf16(TILE, n_keys, 0, 0);   // Q K^T : both K-major from smem
-        mbar_wait_backoff(&k_full[st], (blk >> 1) & 1);
         tc_fence_after();
         const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * Q_BYTES), 16, 1024, 2);
         const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * Q_BYTES), 16, 1024, 2);
@@ -265,6 +264,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int hi = 0; hi < nh; ++hi) {
         const int qs = hi & 1;
         mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
+        mbar_wait_backoff(&k_full[it & 1], (it >> 1) & 1);
         if (it > 0) mbar_wait_backoff(s_free, (it - 1) & 1);            // previous head's last S is in registers
         issue_s(qs, it, 0);
         if (n_kv == 1) umma_commit(&q_empty[qs]);
@@ -273,16 +273,19 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const int st = cur & 1;
           tr_n = cur;
           TRACE_STAMP(0);
+          // (the TMA barriers are polled BEFORE the softmax-dependent ones: every poll costs ~100 cycles while the
+          //  MIO queue is full of MUFU work, and these are off the S -> P -> O critical path)
           if (j + 1 < n_kv) {
+            mbar_wait_backoff(&k_full[(cur + 1) & 1], ((cur + 1) >> 1) & 1);
             mbar_wait_backoff(s_free, cur & 1);                          // S_j has been copied to registers
             TRACE_STAMP(1);
             issue_s(qs, cur + 1, j + 1);
             TRACE_STAMP(2);
             if (j + 2 == n_kv) umma_commit(&q_empty[qs]);                // last S of this head: Q slot reusable
           }
-          mbar_wait_backoff(p_full, cur & 1);
-          TRACE_STAMP(3);
           mbar_wait_backoff(&v_full[st], (cur >> 1) & 1);
+          TRACE_STAMP(3);
+          mbar_wait_backoff(p_full, cur & 1);
           TRACE_STAMP(4);
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
@@ -316,6 +319,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // a warp whose 32 query rows all lie beyond the end of the sequence keeps the barrier protocol but skips
     // the exponentials and the stores
     const bool rows_ok = q0 + quad * 32 < L;
+    bool s_ready = false;                      // the next block's S barrier was seen complete during the exponentials
     for (int hi = 0; hi < nh; ++hi) {
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int j = 0; j < n_kv; ++j) {
@@ -326,7 +330,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const bool masked = kv_valid < TILE;
         tr_n = cur;
         TRACE_STAMP(0);
-        mbar_wait(s_full, cur & 1);
+        if (!s_ready) mbar_wait(s_full, cur & 1);
         tc_fence_after();
         TRACE_STAMP(1);
         uint32_t s0[32], s1[32], s2[32], s3[32];   // (unconditional loads: conditional asm outputs go to local memory)
@@ -393,11 +397,15 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st16(tP, pk);
           l_sum += exp_pack32<POLY, false>(s1, 32, scale_log2, m_ref, pk);
           tmem_st16(tP + 16, pk);
+          // S_{j+1} was issued when this block's S reached the registers: poll its barrier here, where the
+          // latency of the poll hides behind the remaining exponentials instead of opening the next block
+          s_ready = mbar_try_wait(s_full, (cur + 1) & 1);
           l_sum += exp_pack32<POLY, false>(s2, 32, scale_log2, m_ref, pk);
           tmem_st16(tP + 32, pk);
           l_sum += exp_pack32<POLY, false>(s3, 32, scale_log2, m_ref, pk);
           tmem_st16(tP + 48, pk);
         } else {
+          s_ready = false;
           uint32_t pk[16];
           if (kv_valid > 0) {
             l_sum += exp_pack32<POLY, true>(s0, kv_valid, scale_log2, m_ref, pk);

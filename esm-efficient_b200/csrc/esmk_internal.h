@@ -27,6 +27,9 @@ int softmax(const void* x, int ldx, void* y, int ldy, int T, int V, int log_mode
 
 int gemm(const esmk_gemm_args& a, cudaStream_t st);
 
+int quantize(const void* w, int N, int K, int bits, void* data, float* scale, cudaStream_t st);
+int dequantize(const void* data, const float* scale, int N, int K, int bits, void* w, cudaStream_t st);
+
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
                 const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st);
 

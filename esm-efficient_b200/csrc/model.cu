@@ -1,6 +1,7 @@
 // Whole-model driver: the packed forward pass as a fixed sequence of esmk kernels
 // on one stream (no host synchronisation, CUDA-graph capturable).  Replaces the
 // Python layer loop of esme/esm.py:229-252 and the head of esme/head.py:25-27.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -71,12 +72,26 @@ struct Workspace {
 };
 
 struct Buffers {
-  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb;
+  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb, *wq;
   int32_t *pos, *tile_info;
   size_t bytes;
 };
 
-Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len) {
+// elements of the largest quantised weight of the model (0 = nothing is quantised)
+size_t quant_scratch_elems(const esmk_model* m) {
+  const esmk_config& c = m->cfg;
+  const size_t D = c.embed_dim, F = c.ffn_dim, F1 = c.family == 1 ? 2 * F : F;
+  size_t n = 0;
+  for (const esmk_layer_weights& l : m->layers) {
+    if (l.q_wqkv.data) n = std::max(n, 3 * D * D);
+    if (l.q_wo.data) n = std::max(n, D * D);
+    if (l.q_w1.data) n = std::max(n, F1 * D);
+    if (l.q_w2.data) n = std::max(n, D * F);
+  }
+  return n;
+}
+
+Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len, size_t wq_elems) {
   Workspace w(ws);
   Buffers b;
   const size_t D = c.embed_dim, F = c.ffn_dim, hd = c.embed_dim / c.attention_heads;
@@ -89,6 +104,7 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len) {
   b.sinb = w.take<__nv_bfloat16>((size_t)max_len * hd);
   b.pos = w.take<int32_t>((size_t)T);
   b.tile_info = w.take<int32_t>((size_t)4 * tile_capacity(T, B));
+  b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;
   b.bytes = w.off;
   return b;
 }
@@ -99,6 +115,17 @@ int linear(const void* A, int lda, const void* W, const void* bias, void* C, int
   g.A = A; g.lda = lda; g.W = W; g.bias = bias; g.C = C; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.epilogue = epi; g.R = R; g.ldr = ldr; g.residue_scaling = scale;
   return gemm(g, st);
+}
+
+// the bf16 weight a GEMM should read: the caller's, or the scratch freshly expanded from quantised storage
+int weight_of(const void* w, const esmk_qweight& q, int N, int K, __nv_bfloat16* scratch, cudaStream_t st, const void** out) {
+  if (q.data == nullptr) {
+    *out = w;
+    return 0;
+  }
+  Span span(ESMK_PROF_DEQUANT, st);
+  *out = scratch;
+  return dequantize(q.data, q.scale, N, K, q.bits, scratch, st);
 }
 
 int head_and_output(const esmk_model* m, const __nv_bfloat16* z, int T, __nv_bfloat16* t0, __nv_bfloat16* t1,
@@ -152,8 +179,13 @@ int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out
                "missing model-level weight");
   for (int i = 0; i < cfg->num_layers; ++i) {
     const esmk_layer_weights& l = w->layers[i];
-    ESMK_REQUIRE(l.attn_norm_w && l.attn_norm_b && l.wqkv && l.wo && l.ffn_norm_w && l.ffn_norm_b && l.w1 && l.w2,
-                 "missing layer weight");
+    ESMK_REQUIRE(l.attn_norm_w && l.attn_norm_b && l.ffn_norm_w && l.ffn_norm_b, "missing layer weight");
+    ESMK_REQUIRE((l.wqkv || l.q_wqkv.data) && (l.wo || l.q_wo.data) && (l.w1 || l.q_w1.data) && (l.w2 || l.q_w2.data),
+                 "missing layer weight (neither bf16 nor quantised)");
+    for (const esmk_qweight* q : {&l.q_wqkv, &l.q_wo, &l.q_w1, &l.q_w2})
+      if (q->data) ESMK_REQUIRE(q->scale && (q->bits == 4 || q->bits == 8), "bad quantised weight descriptor");
+    if (l.q_wqkv.data || l.q_wo.data || l.q_w2.data || l.q_w1.data)
+      ESMK_REQUIRE(cfg->embed_dim % 64 == 0 && cfg->ffn_dim % 64 == 0, "quantised weights need dims that are multiples of 64");
     if (cfg->family == 0) ESMK_REQUIRE(l.bqkv && l.bo && l.b1 && l.b2, "ESM2 layers need biases");
     if (cfg->family == 1) ESMK_REQUIRE(l.qln_w && l.kln_w, "ESMC layers need QK-LayerNorm weights");
   }
@@ -167,7 +199,7 @@ int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out
 }
 
 size_t workspace_bytes(const esmk_model* m, int T, int B, int max_len) {
-  return carve(m->cfg, nullptr, T, B, max_len).bytes + 1024;
+  return carve(m->cfg, nullptr, T, B, max_len, quant_scratch_elems(m)).bytes + 1024;
 }
 
 int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T, int B, int max_len,
@@ -178,7 +210,7 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
   ESMK_REQUIRE(kind >= ESMK_OUT_LOGITS && kind <= ESMK_OUT_REPRESENTATION, "bad output kind");
   const esmk_config& c = m->cfg;
   void* ws = reinterpret_cast<void*>(align_up(reinterpret_cast<uintptr_t>(workspace)));
-  Buffers b = carve(c, ws, T, B, max_len);
+  Buffers b = carve(c, ws, T, B, max_len, quant_scratch_elems(m));
   ESMK_REQUIRE(b.bytes + (static_cast<uint8_t*>(ws) - static_cast<uint8_t*>(workspace)) <= workspace_bytes_,
                "workspace too small (see esmk_workspace_bytes)");
   const int D = c.embed_dim, H = c.attention_heads, hd = D / H, F = c.ffn_dim;
@@ -194,27 +226,32 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
     const esmk_layer_weights& l = m->layers[i];
     // ---- attention block: x = x + out(attn(rope(qkv(LN(x))))) / s   (esme/attention.py:126-139, 253-254)
     PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.attn_norm_w, l.attn_norm_b, b.h, D, T, D, 1e-5f, st));
+    const void *wqkv, *wo, *w1, *w2;
+    ESMK_TRY(weight_of(l.wqkv, l.q_wqkv, 3 * D, D, b.wq, st, &wqkv));
     if (fused_rope) {
       esmk_gemm_args g{};
-      g.A = b.h; g.lda = D; g.W = l.wqkv; g.bias = l.bqkv; g.C = b.qkv; g.ldc = 3 * D;
+      g.A = b.h; g.lda = D; g.W = wqkv; g.bias = l.bqkv; g.C = b.qkv; g.ldc = 3 * D;
       g.M = T; g.N = 3 * D; g.K = D; g.epilogue = ESMK_EPI_QKV_ROPE;
       g.rope_cos = b.cosb; g.rope_sin = b.sinb; g.pos = b.pos; g.head_dim = hd; g.rope_cols = 2 * D;
       PROF(ESMK_PROF_GEMM_QKV, gemm(g, st));
     } else {
-      PROF(ESMK_PROF_GEMM_QKV, linear(b.h, D, l.wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
+      PROF(ESMK_PROF_GEMM_QKV, linear(b.h, D, wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
       PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
     }
     PROF(ESMK_PROF_ATTENTION,
          attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));
-    PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, l.wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    ESMK_TRY(weight_of(l.wo, l.q_wo, D, D, b.wq, st, &wo));
+    PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)
     PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));
+    ESMK_TRY(weight_of(l.w1, l.q_w1, c.family == 0 ? F : 2 * F, D, b.wq, st, &w1));
     if (c.family == 0) {
-      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, l.w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
+      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
     } else {
-      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, l.w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
+      PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
     }
-    PROF(ESMK_PROF_GEMM_FFN_DOWN, linear(b.u, F, l.w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    ESMK_TRY(weight_of(l.w2, l.q_w2, D, F, b.wq, st, &w2));
+    PROF(ESMK_PROF_GEMM_FFN_DOWN, linear(b.u, F, w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     if (layer_taps != nullptr && layer_taps[i] != nullptr)
       ESMK_CUDA(cudaMemcpyAsync(layer_taps[i], b.x, (size_t)T * D * 2, cudaMemcpyDeviceToDevice, st));
   }

@@ -45,10 +45,16 @@ class Config(C.Structure):
     ]
 
 
+class QWeight(C.Structure):
+    """esmk_qweight: optional quantised storage of one weight (data NULL = not quantised)."""
+    _fields_ = [('data', c_void_p), ('scale', c_void_p), ('bits', c_int)]
+
+
 class LayerWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
         'attn_norm_w', 'attn_norm_b', 'wqkv', 'bqkv', 'qln_w', 'kln_w', 'wo', 'bo',
-        'ffn_norm_w', 'ffn_norm_b', 'w1', 'b1', 'w2', 'b2')]
+        'ffn_norm_w', 'ffn_norm_b', 'w1', 'b1', 'w2', 'b2')] + \
+        [(n, QWeight) for n in ('q_wqkv', 'q_wo', 'q_w1', 'q_w2')]
 
 
 class Weights(C.Structure):
@@ -79,6 +85,8 @@ SIGNATURES = {
     'esmk_mean_pool': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     'esmk_softmax': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_gemm': (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    'esmk_quantize': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'esmk_dequantize': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'esmk_attn_varlen': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_model_create': (c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(c_void_p)]),
@@ -104,7 +112,7 @@ def check(rc: int, what: str):
 
 
 PROF_CATEGORIES = ('misc', 'layernorm', 'gemm_qkv', 'rope', 'attention', 'gemm_out', 'gemm_ffn_up',
-                   'gemm_ffn_down', 'head')
+                   'gemm_ffn_down', 'head', 'dequant')
 
 
 def profile_enable(on: bool):

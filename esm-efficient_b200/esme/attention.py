@@ -17,6 +17,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import ops
+from .quantization import dense_weight
 from .rotary import RotaryEmbedding
 
 
@@ -45,7 +46,7 @@ class SwiGLU(nn.Module):
             .reshape(2 * F_, D).contiguous()
 
     def forward(self, x: Tensor) -> Tensor:
-        w = self.interleave(self.activation.weight, self.fc.weight)
+        w = self.interleave(dense_weight(self.activation), dense_weight(self.fc))
         return ops.linear(x, w, None, epilogue=L.EPI_SWIGLU)
 
 
@@ -79,7 +80,7 @@ class FlashMultiheadAttention(nn.Module):
 
     def packed_qkv(self):
         """Concatenated [3D,D] weight and [3D] bias (or None) for the single QKV GEMM."""
-        w = torch.cat((self.q.weight, self.k.weight, self.v.weight), dim=0).contiguous()
+        w = torch.cat((dense_weight(self.q), dense_weight(self.k), dense_weight(self.v)), dim=0).contiguous()
         b = None
         if self.q.bias is not None:
             b = torch.cat((self.q.bias, self.k.bias, self.v.bias), dim=0).contiguous()
@@ -117,7 +118,7 @@ class FlashMultiheadAttention(nn.Module):
         _reject_lora(lora_names)
         qkv, tile_info = self._qkv_rot(x, cu_lens, max_len)
         a = self._attn(qkv, cu_lens, max_len, tile_info)
-        return ops.linear(a, self.out.weight, self.out.bias)
+        return ops.linear(a, dense_weight(self.out), self.out.bias)
 
 
 class FlashTransformerLayer(nn.Module):
@@ -158,13 +159,13 @@ class FlashTransformerLayer(nn.Module):
         qkv, tile_info = sa._qkv_rot(x, cu_lens, max_len)
         a = sa._attn(qkv, cu_lens, max_len, tile_info)
         # x + out(a) / s, fused into the out-projection epilogue
-        x = ops.linear(a, sa.out.weight, sa.out.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
+        x = ops.linear(a, dense_weight(sa.out), sa.out.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
         ln = self.final[0]
         h = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
         if self.final_activation == 'gelu':
-            u = ops.linear(h, self.final[1].weight, self.final[1].bias, epilogue=L.EPI_BIAS_GELU)
+            u = ops.linear(h, dense_weight(self.final[1]), self.final[1].bias, epilogue=L.EPI_BIAS_GELU)
             down = self.final[3]
         else:
             u = self.final[1](h)
             down = self.final[2]
-        return ops.linear(u, down.weight, down.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
+        return ops.linear(u, dense_weight(down), down.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)

@@ -17,6 +17,7 @@ from . import ops
 from .alphabet import Alphabet, Alphabet3
 from .attention import FlashTransformerLayer, SwiGLU
 from .head import RobertaLMHead
+from .quantization import _QuantLinear, dense_weight, quantize_model_
 
 model_names = ['esm2_8m', 'esm2_35m', 'esm2_150m', 'esm2_650m', 'esm2_3b', 'esm2_15b',
                'esmc_300m', 'esmc_600m', 'esm1b', 'esm1v_1', 'esm1v_2', 'esm1v_3', 'esm1v_4', 'esm1v_5']
@@ -58,24 +59,25 @@ class _Engine:
         layers = (L.LayerWeights * model.num_layers)()
         for i, layer in enumerate(model.layers):
             sa, lw = layer.self_attn, layers[i]
-            wqkv, bqkv = sa.packed_qkv()
-            self.keep += [wqkv] + ([bqkv] if bqkv is not None else [])
             lw.attn_norm_w, lw.attn_norm_b = sa.norm.weight.data_ptr(), sa.norm.bias.data_ptr()
-            lw.wqkv, lw.bqkv = wqkv.data_ptr(), ops._ptr(bqkv)
+            lw.wqkv = self._weight((sa.q, sa.k, sa.v), lw.q_wqkv)
+            bqkv = None
+            if sa.q.bias is not None:
+                bqkv = torch.cat((sa.q.bias, sa.k.bias, sa.v.bias), dim=0).contiguous()
+                self.keep.append(bqkv)
+            lw.bqkv = ops._ptr(bqkv)
             lw.qln_w = sa.layernorm_q.weight.data_ptr() if sa.pre_layernorm else None
             lw.kln_w = sa.layernorm_k.weight.data_ptr() if sa.pre_layernorm else None
-            lw.wo, lw.bo = sa.out.weight.data_ptr(), ops._ptr(sa.out.bias)
+            lw.wo, lw.bo = self._weight((sa.out,), lw.q_wo), ops._ptr(sa.out.bias)
             ln = layer.final[0]
             lw.ffn_norm_w, lw.ffn_norm_b = ln.weight.data_ptr(), ln.bias.data_ptr()
             if family == 0:
                 up, down = layer.final[1], layer.final[3]
-                lw.w1, lw.b1 = up.weight.data_ptr(), ops._ptr(up.bias)
+                lw.w1, lw.b1 = self._weight((up,), lw.q_w1), ops._ptr(up.bias)
             else:
                 glu, down = layer.final[1], layer.final[2]
-                w1 = SwiGLU.interleave(glu.activation.weight.detach(), glu.fc.weight.detach())
-                self.keep.append(w1)
-                lw.w1, lw.b1 = w1.data_ptr(), None
-            lw.w2, lw.b2 = down.weight.data_ptr(), ops._ptr(down.bias)
+                lw.w1, lw.b1 = self._weight((glu.activation, glu.fc), lw.q_w1, interleave=True), None
+            lw.w2, lw.b2 = self._weight((down,), lw.q_w2), ops._ptr(down.bias)
         w = L.Weights()
         w.embed = model.embed_tokens.weight.data_ptr()
         w.layers = layers
@@ -95,6 +97,33 @@ class _Engine:
         self._layers_struct = layers
         self.workspace: Optional[torch.Tensor] = None
         self.stamp = _stamp(model)
+
+    def _weight(self, mods, qdesc, interleave=False):
+        """Device pointer of the bf16 weight the GEMM reads -- the row-wise concatenation (or, for the SwiGLU
+        pair, the 32-row interleave) of the modules' weights -- or None after filling `qdesc` when all of them
+        are quantised alike, in which case their packed storage is concatenated / interleaved the same way
+        (every format keeps whole rows together, so row operations commute with quantisation)."""
+        join = (lambda a, b: SwiGLU.interleave(a, b)) if interleave else None
+        quant = [isinstance(m, _QuantLinear) for m in mods]
+        if all(quant) and len({m.bits for m in mods}) == 1:
+            rows = [m.out_features for m in mods]
+            datas = [m.weight.data.reshape(r, -1) for m, r in zip(mods, rows)]
+            scales = [m.scale.reshape(r, -1) for m, r in zip(mods, rows)]
+            if len(mods) == 1:
+                data, scale = datas[0], scales[0]
+            elif interleave:
+                data, scale = join(*datas), join(*scales)
+            else:
+                data, scale = torch.cat(datas, 0).contiguous(), torch.cat(scales, 0).contiguous()
+            self.keep += [data, scale]
+            qdesc.data, qdesc.scale, qdesc.bits = data.data_ptr(), scale.data_ptr(), mods[0].bits
+            return None
+        ws = [dense_weight(m).detach() for m in mods]
+        if len(mods) == 1 and not quant[0]:
+            return ws[0].data_ptr()                          # the parameter itself, no copy
+        w = ws[0] if len(mods) == 1 else (join(*ws) if interleave else torch.cat(ws, 0).contiguous())
+        self.keep.append(w)
+        return w.data_ptr()
 
     def __del__(self):
         try:
@@ -302,7 +331,9 @@ class ESM2(nn.Module):
             f'load_in must be one of [None, "8bit", "4bit"] but got {quantization}'
         if quantization is not None:
             assert device != 'cpu', 'Quantized model cannot be loaded on cpu provide CUDA gpu device'
-            raise NotImplementedError('weight-quantized loading (bitsandbytes formats) is not part of this build yet')
+            if quantization == '8bitexperimental':
+                raise NotImplementedError("'8bitexperimental' (esme/quantization.py, needs torch_cublas_matmul_int8; "
+                                          "its tests are skipped in the reference) is not part of this build")
         device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
         with torch.device('meta'):
             model = cls.create_model(path, checkpointing=checkpointing)
@@ -323,7 +354,12 @@ class ESM2(nn.Module):
         for m in model.modules():           # non-persistent buffers are not materialised by to_empty
             if hasattr(m, 'inv_freq'):
                 m.inv_freq = 1.0 / (m.base ** (torch.arange(0, m.dim, 2, device=device, dtype=torch.float32) / m.dim))
-        return model.eval().requires_grad_(False)
+        model = model.eval().requires_grad_(False)
+        if quantization is not None:
+            # esme/esm.py:449-472 / 916-946: q, k, v, out and the FFN linears become weight-quantised modules
+            # (this library's formats, see esme/quantization.py); biases, LayerNorms, embedding, LM head stay bf16
+            quantize_model_(model, 4 if quantization == '4bit' else 8)
+        return model
 
 
 class ESMC(ESM2):

@@ -173,3 +173,30 @@ def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torc
                                    cu_lens.data_ptr(), tile_info.data_ptr(), B, T, H, hd, int(max_len), impl,
                                    _stream()), 'esmk_attn_varlen')
     return out
+
+
+def quantize(weight: torch.Tensor, bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16 [N,K] weight -> (data, scale) in the library's weight-only formats (include/esmk.h):
+    bits=4: uint8 [N*K/2, 1] + fp32 absmax [N*K/64];  bits=8: int8 [N,K] + fp32 [N] (row absmax / 127)."""
+    _need_cuda(weight)
+    assert weight.dtype == bf16 and weight.ndim == 2 and bits in (4, 8)
+    w = weight.contiguous()
+    N, K = w.shape
+    if bits == 4:
+        data = torch.empty(N * K // 2, 1, dtype=torch.uint8, device=w.device)
+        scale = torch.empty(N * K // 64, dtype=torch.float32, device=w.device)
+    else:
+        data = torch.empty(N, K, dtype=torch.int8, device=w.device)
+        scale = torch.empty(N, dtype=torch.float32, device=w.device)
+    L.check(L.lib.esmk_quantize(w.data_ptr(), N, K, bits, data.data_ptr(), scale.data_ptr(), _stream()), 'esmk_quantize')
+    return data, scale
+
+
+def dequantize(data: torch.Tensor, scale: torch.Tensor, N: int, K: int, bits: int) -> torch.Tensor:
+    """Inverse of `quantize`: bf16 [N,K]."""
+    _need_cuda(data, scale)
+    assert data.is_contiguous() and scale.is_contiguous() and scale.dtype == torch.float32
+    w = torch.empty(N, K, dtype=bf16, device=data.device)
+    L.check(L.lib.esmk_dequantize(data.data_ptr(), scale.data_ptr(), N, K, bits, w.data_ptr(), _stream()),
+            'esmk_dequantize')
+    return w

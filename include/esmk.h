@@ -131,6 +131,25 @@ ESMK_API int esmk_attn_varlen(const void* q, const void* k, const void* v, int l
                      const int32_t* cu_lens, const int32_t* tile_info, int B, int T, int H, int head_dim,
                      int max_len, int impl, esmk_stream_t stream);
 
+/* ---- weight-only quantised storage --------------------------------------- */
+/* Replaces the bitsandbytes modules the reference's quantised loaders install for q, k, v, out and the two
+ * FFN linears (esme/esm.py:414-472 `_load_linear4bit` / `_load_linear8bit` / `_load_quantize`, ESMC :916-946).
+ * bitsandbytes is not part of /root/reference; the formats are this library's (parity unpinned):
+ *   bits = 4: `data` uint8[N*K/2], two 4-bit codes per byte, EVEN element in the high nibble; code = sign (8) |
+ *             index into {0, 1/192, 2/3, 1, 1/3, 1/2, 1/6, 1/4} (bitsandbytes' fp4 codebook); `scale` fp32[N*K/64]
+ *             = absmax of each block of 64 consecutive weights (K % 64 == 0; no double quantisation)
+ *   bits = 8: `data` int8[N,K]; `scale` fp32[N] = row absmax / 127
+ * W is the bf16 [N,K] nn.Linear weight.  As in bitsandbytes' batched path the GEMM itself runs in bf16 on the
+ * dequantised weight. */
+ESMK_API int esmk_quantize(const void* W, int N, int K, int bits, void* data, float* scale, esmk_stream_t stream);
+ESMK_API int esmk_dequantize(const void* data, const float* scale, int N, int K, int bits, void* W, esmk_stream_t stream);
+
+typedef struct {
+  const void* data;   /* NULL = this weight is not quantised */
+  const float* scale;
+  int bits;           /* 4 or 8 */
+} esmk_qweight;
+
 /* ---- whole model --------------------------------------------------------- */
 typedef struct {
   int family;          /* 0 = ESM2 (bias, GELU FFN, mask-row zeroing), 1 = ESMC (QK-LN, SwiGLU, residue scaling) */
@@ -146,6 +165,10 @@ typedef struct {
   const void *ffn_norm_w, *ffn_norm_b;
   const void *w1, *b1;           /* ESM2 [F,D]; ESMC interleaved [2F,D] */
   const void *w2, *b2;           /* [D,F] */
+  /* optional quantised storage of wqkv / wo / w1 / w2 (same shapes and row order as the bf16 weight it
+   * replaces, whose pointer may then be NULL): esmk_forward expands it into workspace scratch right before
+   * the GEMM that consumes it */
+  esmk_qweight q_wqkv, q_wo, q_w1, q_w2;
 } esmk_layer_weights;
 
 typedef struct {
@@ -197,7 +220,8 @@ enum esmk_prof_category {
   ESMK_PROF_GEMM_FFN_UP = 6,
   ESMK_PROF_GEMM_FFN_DOWN = 7,
   ESMK_PROF_HEAD = 8,          /* LM head (2 GEMMs + LayerNorm + softmax) */
-  ESMK_PROF_COUNT = 9
+  ESMK_PROF_DEQUANT = 9,       /* quantised weight -> bf16 scratch */
+  ESMK_PROF_COUNT = 10
 };
 /* When enabled, esmk_forward brackets every launch with CUDA events on its stream.
  * esmk_profile_read (after the caller synchronised the stream) returns the summed
