@@ -207,6 +207,22 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// TMA store (shared::cta -> global) in the thread's bulk async-group; out-of-bounds rows / columns of the box
+// are clipped by the tensor map.  The smem writes must be made visible to the async proxy first
+// (fence_proxy_async_smem by every writing thread, then a warp / CTA sync before the issuing thread).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest `N` bulk groups of this thread have finished READING shared memory (the source may be reused)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// all bulk groups of this thread are complete (global writes performed)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // createpolicy-style constants used by CUTLASS (TMA::CacheHintSm90)
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;

@@ -32,7 +32,15 @@ __host__ __device__ constexpr int epi_warps(int epi) {
 }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + epi_warps(epi) * 32; }
 constexpr int STAGES_PAIR = 6;         // 2-CTA mode: 16 KB A + 16 KB half-W per stage
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+// Output staging for the TMA-store epilogue: one private slot per epilogue warp (16 x 2 KB = 32 rows x 32 columns,
+// or 8 x 4 KB = 32 rows x 64 columns), written with the TMA swizzle pattern and drained by cp.async.bulk.tensor
+// stores: whole 128-byte lines leave the SM through the TMA unit instead of 16-byte-per-row scattered STGs that
+// compete with the operand loads for the LSU / L1 path (ncu: 72 % l1tex throughput, `lg` stalls, and tensor-pipe
+// activity falling with output bytes per FLOP before this change).
+constexpr int STORE_STAGING = 32 * 1024;
+constexpr int BAR_REGION = 1024;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_REGION + STORE_STAGING + 1024 /*align slack*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGES_PAIR * (A_STAGE + B_STAGE / 2) == STAGES * (A_STAGE + B_STAGE), "same smem footprint");
 
 struct EpiParams {
@@ -47,6 +55,7 @@ struct EpiParams {
   const int32_t* pos;
   int rope_cols;
   int vec_ok;  // 16-byte accesses allowed on C / R / bias (alignment and N % 8 == 0)
+  int tma_store;  // tmC is valid: whole 64-column groups leave through shared memory + TMA stores
 };
 
 // exact-erf GELU:  gelu(x) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2,
@@ -207,8 +216,8 @@ __device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const uint32_t 
 
 template <int EPI, int HD, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-            EpiParams ep) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiParams ep) {
   constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
   constexpr int BSTAGE = PAIR ? B_STAGE / 2 : B_STAGE;
@@ -222,6 +231,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_full = bars + 2 * NSTAGE; // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* store_slot = smem + NSTAGE * (A_STAGE + BSTAGE) + BAR_REGION +
+                        (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * (STORE_STAGING / EPI_WARPS) : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (ep.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);   // pair: the leader arms it with the bytes of BOTH CTAs' loads
       mbar_init(&empty[s], 1);
@@ -402,9 +414,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 16; ++j)
               w[j] = pack_bf16(gelu_fast(bf16_lo(w[j])), gelu_fast(bf16_hi(w[j])));
           }
-          if (!row_ok) continue;
+          if (!row_ok && !ep.tma_store) continue;
           if constexpr (EPI == ESMK_EPI_RESIDUAL) {
-            if (ep.scale == 1.0f) {                                              // bf(x + y), packed
+            if (!row_ok) {                                                       // (clipped by the TMA store)
+            } else if (ep.scale == 1.0f) {                                       // bf(x + y), packed
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 r = rq[c * 4 + j];
@@ -426,9 +439,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          uint4* dst4 = reinterpret_cast<uint4*>(ep.C + (size_t)row * ep.ldc + col0);
+          if (ep.tma_store) {
+            // 32 rows x 64 bytes, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+            if (lane == 0) tma_store_wait_read<0>();       // the previous store out of this slot has been read
+            __syncwarp();
+            uint8_t* srow = store_slot + lane * 64;
+            const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, store_slot, col0, m0 + quad * 32);
+              tma_store_commit();
+            }
+          } else {
+            uint4* dst4 = reinterpret_cast<uint4*>(ep.C + (size_t)row * ep.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
         } else {
           // ---- ragged right edge or unaligned operands: element-wise (compile-time indices keep v[] in registers)
           if (!row_ok) continue;
@@ -594,6 +624,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   w[4 * j + 3] = badd2(rq[j].w, w[4 * j + 3]);
                 }
               }
+            }
+            if (ep.tma_store) {
+              // 32 rows x 128 bytes, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+              uint8_t* srow = store_slot + lane * 128;
+              const int sw = lane & 7;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmC, store_slot, col0, m0 + quad * 32);
+                tma_store_commit();
+              }
+            } else if (row_ok) {
               uint4* dst4 = reinterpret_cast<uint4*>(ep.C + (size_t)row * ep.ldc + col0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst4[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
@@ -623,7 +670,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float sl = bfr(__fdividef(a, 1.0f + __expf(-a)));
             o[j] = sl * v[32 + j];
           }
-          if (row_ok) {
+          if (ep.tma_store && full_group) {
+            // 32 rows x 64 bytes (32 output columns), SWIZZLE_64B
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            uint8_t* srow = store_slot + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = pack_u4(o + 8 * j);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, store_slot, col0 >> 1, m0 + quad * 32);
+              tma_store_commit();
+            }
+          } else if (row_ok) {
             const int oc0 = col0 >> 1;
             const int No = N >> 1;
             __nv_bfloat16* dst = ep.C + (size_t)row * ep.ldc + oc0;
@@ -674,6 +735,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait_all();   // this warp's bulk stores have been written
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -692,8 +754,8 @@ bool use_pair_mode() {
 }
 
 template <int EPI, int HD, bool PAIR>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& ep,
-                cudaStream_t st) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                const EpiParams& ep, cudaStream_t st) {
   auto kern = gemm_kernel<EPI, HD, PAIR>;
   static bool configured = false;
   if (!configured) {
@@ -719,7 +781,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, in
   cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, ep));
+  ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, ep));
   count_launch();
   return 0;
 }
@@ -748,32 +810,43 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   const int n_out = a.epilogue == ESMK_EPI_SWIGLU ? a.N / 2 : a.N;
   ep.vec_ok = (n_out % 8 == 0) && (a.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
   if (a.bias != nullptr) ep.vec_ok = ep.vec_ok && ((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
+  if (a.epilogue == ESMK_EPI_RESIDUAL)
+    ep.vec_ok = ep.vec_ok && a.R != nullptr && (a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+  // output tensor map of the TMA-store epilogue: 32-row boxes of one warp's column chunk
+  CUtensorMap tmC = tmA;
+  static const bool tma_store_enabled = [] { const char* e = getenv("ESMK_GEMM_TMA_STORE"); return e == nullptr || e[0] != '0'; }();
+  ep.tma_store = 0;
+  if (ep.vec_ok && tma_store_enabled) {
+    const bool wide = a.epilogue == ESMK_EPI_QKV_ROPE;          // 8-warp epilogue, 64-column groups
+    ESMK_TRY(make_tmap_2d(&tmC, a.C, a.M, n_out, a.ldc, 32, wide ? 64 : 32, wide ? 128 : 64));
+    ep.tma_store = 1;
+  }
   switch (a.epilogue) {
     case ESMK_EPI_BIAS:
-      return pair ? launch_impl<ESMK_EPI_BIAS, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_BIAS, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_BIAS_GELU:
-      return pair ? launch_impl<ESMK_EPI_BIAS_GELU, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_BIAS_GELU, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS_GELU, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS_GELU, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_RESIDUAL:
       ESMK_REQUIRE(a.R != nullptr && a.residue_scaling != 0.f, "residual epilogue needs R and a non-zero scale");
       ep.vec_ok = ep.vec_ok && (a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
-      return pair ? launch_impl<ESMK_EPI_RESIDUAL, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_RESIDUAL, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_RESIDUAL, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_RESIDUAL, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_SWIGLU:
       ESMK_REQUIRE(a.N % 64 == 0, "SwiGLU epilogue needs N (= 2F) to be a multiple of 64");
       ESMK_REQUIRE(a.bias == nullptr, "SwiGLU epilogue has no bias (ESMC linears are bias-free)");
-      return pair ? launch_impl<ESMK_EPI_SWIGLU, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_SWIGLU, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_SWIGLU, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_SWIGLU, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_QKV_ROPE:
       ESMK_REQUIRE(a.rope_cos && a.rope_sin && a.pos, "QKV_ROPE epilogue needs cos/sin tables and positions");
       ESMK_REQUIRE(a.rope_cols % 64 == 0 && a.rope_cols <= a.N, "rope_cols must be a multiple of 64 and <= N");
-      if (a.head_dim == 64) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 64, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 64, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 32) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 32, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 32, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 16) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 16, true>(tmA, tmB, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 16, false>(tmA, tmB, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 64) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 32) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 32, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 32, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 16) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 16, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 16, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
       return fail("esmk_gemm", "fused QKV_ROPE supports head_dim 16/32/64; use ESMK_EPI_BIAS + esmk_qk_norm_rope");
     default:
       return fail("esmk_gemm", "unknown epilogue");

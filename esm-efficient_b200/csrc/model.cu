@@ -170,7 +170,8 @@ int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out
   ESMK_REQUIRE(cfg->embed_dim % cfg->attention_heads == 0, "embed_dim must be divisible by attention_heads");
   ESMK_REQUIRE(cfg->embed_dim % 8 == 0 && cfg->ffn_dim % 8 == 0, "embed_dim / ffn_dim must be multiples of 8");
   const int hd = cfg->embed_dim / cfg->attention_heads;
-  ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "head_dim must be 16, 32, 64 or 128");
+  ESMK_REQUIRE(hd % 8 == 0 && hd >= 8 && hd <= 128, "head_dim must be a multiple of 8, at most 128");
+  if (cfg->family == 1) ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "ESMC head_dim must be 16, 32, 64 or 128");
   ESMK_REQUIRE(cfg->vocab >= 1 && cfg->vocab <= 128 && cfg->embed_rows >= cfg->vocab - 0, "bad vocab");
   ESMK_REQUIRE(cfg->residue_scaling > 0.f, "residue_scaling must be positive");
   if (cfg->family == 1) ESMK_REQUIRE(cfg->ffn_dim % 32 == 0, "ESMC ffn_dim must be a multiple of 32");
@@ -215,7 +216,7 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
                "workspace too small (see esmk_workspace_bytes)");
   const int D = c.embed_dim, H = c.attention_heads, hd = D / H, F = c.ffn_dim;
   const float s = c.residue_scaling;
-  const bool fused_rope = (c.family == 0) && (hd <= 64) && ((2 * D) % 64 == 0);
+  const bool fused_rope = (c.family == 0) && (hd == 16 || hd == 32 || hd == 64) && ((2 * D) % 64 == 0);
 
   PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_info, st));
   PROF(ESMK_PROF_MISC, rope_tables(b.cosb, b.sinb, max_len, hd, st));

@@ -319,6 +319,28 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
   }
 }
 
+// Rotation for head dims whose half is not a whole number of 8-element groups (ESM2-35M: hd = 24): one thread
+// per (token, q|k, head, pair i < hd/2); same rounding points as above.  Small models only.
+__global__ void __launch_bounds__(256)
+rope_pairs_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int ld, int T, int H, int hd,
+                  const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
+                  const int32_t* __restrict__ pos) {
+  const int half = hd >> 1;
+  const long n = (long)T * H * half;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = (int)(i % half);
+  const int h = (int)((i / half) % H);
+  const int t = (int)(i / ((long)half * H));
+  __nv_bfloat16* x = (blockIdx.y == 0 ? q : k) + (size_t)t * ld + h * hd;
+  const int p = pos[t];
+  const float c0 = __bfloat162float(cosb[(size_t)p * hd + d]), c1 = __bfloat162float(cosb[(size_t)p * hd + d + half]);
+  const float s0 = __bfloat162float(sinb[(size_t)p * hd + d]), s1 = __bfloat162float(sinb[(size_t)p * hd + d + half]);
+  const float a = __bfloat162float(x[d]), b = __bfloat162float(x[d + half]);
+  x[d] = __float2bfloat16_rn(bfr(a * c0) + bfr(-b * s0));          // rotate_half: [-x2, x1]
+  x[d + half] = __float2bfloat16_rn(bfr(b * c1) + bfr(a * s1));
+}
+
 template <int NCH>
 static void launch_qk(void* q, void* k, int ld, int T, int D, int hd, const void* lnq, const void* lnk,
                       const void* cosb, const void* sinb, const int32_t* pos, cudaStream_t st) {
@@ -331,7 +353,19 @@ static void launch_qk(void* q, void* k, int ld, int T, int D, int hd, const void
 int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,
                  const void* sinb, const int32_t* pos, cudaStream_t st) {
   const int D = H * hd;
-  ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "rotary head_dim must be 16, 32, 64 or 128");
+  if (!(hd == 16 || hd == 32 || hd == 64 || hd == 128)) {
+    ESMK_REQUIRE(hd % 2 == 0 && hd >= 2, "rotary head_dim must be even");
+    ESMK_REQUIRE(lnq == nullptr && lnk == nullptr, "QK-LayerNorm is only built for head_dim 16, 32, 64, 128");
+    ESMK_REQUIRE(cosb != nullptr && sinb != nullptr && pos != nullptr, "cos, sin and positions required");
+    if (T == 0) return 0;
+    const long n = (long)T * H * (hd / 2);
+    dim3 grid((unsigned)((n + 255) / 256), 2);
+    rope_pairs_kernel<<<grid, 256, 0, st>>>((__nv_bfloat16*)q, (__nv_bfloat16*)k, ld, T, H, hd,
+                                            (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, pos);
+    count_launch();
+    ESMK_CUDA(cudaGetLastError());
+    return 0;
+  }
   ESMK_REQUIRE(ld % 8 == 0 && D <= 20 * 256, "bad q/k pitch or embed_dim > 5120");
   ESMK_REQUIRE((cosb == nullptr) == (sinb == nullptr), "cos and sin must be given together");
   ESMK_REQUIRE(cosb == nullptr || pos != nullptr, "positions required for rotary");
