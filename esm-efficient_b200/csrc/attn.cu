@@ -8,15 +8,25 @@
 //   warp 0     : TMA producer (Q per head; K_j, V_j 128x64 bf16 tiles, SWIZZLE_128B, all double-buffered)
 //   warp 1     : tcgen05.mma issuer:  S = Q K_j^T   (SS UMMA 128x128x16, K-major smem operands)
 //                                      O += P_j V_j  (TS UMMA 128x64x16: P read from TENSOR MEMORY, V MN-major smem)
-//   warps 2..9 : softmax, TWO threads per query row (each owns 64 of the block's 128 keys and 32 of the
-//                64 O columns): one TMEM read of S per block, row maximum exchanged through shared memory,
-//                P = exp2(S*c - m) rounded to bf16 and written back to TMEM (tcgen05.st).
+//   warps 2..5 : softmax, ONE thread per query row (128 S values in registers): one TMEM read of S per block,
+//                row maximum without any cross-thread exchange, P = exp2(S*c - m) rounded to bf16 and written
+//                back to TMEM (tcgen05.st), one barrier arrival per warp.
 //   TMEM (256 columns): S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256)
 //   - S_{j+1} is issued as soon as the softmax warps hold S_j in registers (s_free), so it overlaps the
 //     exponentials of block j; no P staging in shared memory;
 //   - O accumulates in TMEM and is rescaled lazily: only when a row maximum grows by more than 2^8 over the
-//     reference maximum its P values were scaled with (P <= 256 keeps bf16's relative precision, row sums
-//     stay in fp32), so the steady state is bound by the exponentials (MUFU), not by corrections.
+//     reference maximum its P values were scaled with (P is a bf16 FLOAT: its relative precision does not
+//     depend on the reference; row sums stay in fp32);
+//   - the last key block of a sequence is trimmed: the S MMA runs with N = valid keys rounded up to 16, the
+//     P.V MMA with as many 16-key steps, and the softmax warps skip 32-column chunks without valid keys;
+//     warps whose 32 query rows lie beyond the sequence end only keep the barrier protocol.
+// The kernel is bound by the exponentials: 128x128 ex2 per block at 16 MUFU/clk/SM = 1024 cycles against
+// 512 tensor cycles (tools/microbench/pipes.cu, profiles/r1_microbench_pipes.txt).  Every other instruction
+// that goes through the MIO queue (mbarrier polls, shared memory, TMEM loads/stores) queues behind the MUFU
+// work of the co-resident CTA (~100-250 cycles each), so the per-block protocol is kept minimal.  A software
+// exp2 on the FMA pipes (exp_pack32, POLY > 0) was measured and does NOT pay at head_dim 64: the FMA/ALU
+// pipes and the issue slots saturate at the same time as the MUFU unit; it is compiled in
+// behind ESMK_ATTN_POLY for A/B runs and off by default.
 //
 // attn_generic_kernel: CUDA-core kernel for other head dims (e.g. ESM2-8M, hd=16) and the on-device
 // cross-check of the tcgen05 kernel.

@@ -369,6 +369,47 @@ def attn_probe():
 
 
 @case
+def perf_attn_cold():
+    """Attention kernel timed per launch with CUDA events, (a) back to back, (b) after streaming 1 GB through L2
+    (as inside a forward, where the QKV GEMM has just pushed ~0.5 GB through the 126 MB L2)."""
+    import subprocess
+    torch, ops, L, O = _imports()
+    dev = 'cuda'
+    out = {}
+    lens = O.synthetic_lengths(50000, seed=2)
+    T, H, hd = sum(lens), 20, 64
+    D = H * hd
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    cu = cu.to(dev)
+    qkv = torch.randn(T, 3 * D, device=dev).bfloat16()
+    q, k, v = (qkv[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    flops = 4.0 * D * sum(l * l for l in lens)
+    _, tile_info = ops.batch_meta(cu, T)
+    junk = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    for cold in (False, True):
+        ts = []
+        for i in range(13):
+            if cold:
+                junk.add_(1)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            ops.attn_varlen(q, k, v, cu, max(lens), tile_info, impl=0)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        out['cold_l2' if cold else 'back_to_back'] = dict(ms=ms, tflops=flops / ms / 1e9)
+    try:
+        out['sm_clock_mhz_after'] = subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm', '--format=csv,noheader,nounits'],
+                                                   capture_output=True, text=True).stdout.strip()
+    except Exception:
+        pass
+    return out
+
+
+@case
 def perf_attn():
     torch, ops, L, O = _imports()
     dev = 'cuda'
