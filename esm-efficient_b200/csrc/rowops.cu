@@ -23,6 +23,19 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
+// packed bf16x2 arithmetic: exactly torch's bf16 elementwise ops (one RNE rounding per op)
+__device__ __forceinline__ uint32_t bmul2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t badd2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bsub2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hsub2_rn(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
@@ -267,6 +280,10 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
       for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
     }
   }
+  // From here on the row lives as packed bf16x2 words (4 per 8-element group): the roundings of the reference's
+  // bf16 elementwise ops are done by the packed conversions / HMUL2.BF16 / HADD2.BF16 instructions instead of
+  // scalar F2F conversions, which issue on the 16-lane XU pipe and made this kernel compute-bound.
+  uint4 pk[NCH];
   if (lnw != nullptr) {  // ESMC: q = bf(LN_w(q)) over the full embedding dim
     const float mean = warp_sum(sum) / (float)D;
     float sq = 0.f;
@@ -281,13 +298,18 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       int idx = c * 32 + lane;
+      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (idx < D8) {
         float wf[8];
         unpack8(__ldg(w4 + idx), wf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[c][j] = bfr((v[c][j] - mean) * rstd * wf[j]);
+        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * wf[j];
       }
+      pk[c] = pack8(o);
     }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pk[c] = pack8(v[c]);   // exact: the values are bf16 already
   }
   if (cosb != nullptr) {
     const int p = pos[row];
@@ -299,23 +321,36 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
     for (int c = 0; c < NCH; ++c) {
       int idx = c * 32 + lane;
       int o = (idx * 8) % hd;  // offset of this 8-element group inside its head
-      float cf[8], sf[8];
+      uint4 cw = make_uint4(0, 0, 0, 0), sw = cw;
       if (idx < D8) {
-        unpack8(__ldg(c4 + (o >> 3)), cf);
-        unpack8(__ldg(s4 + (o >> 3)), sf);
+        cw = __ldg(c4 + (o >> 3));
+        sw = __ldg(s4 + (o >> 3));
       }
-      const float sign = (o < half) ? -1.f : 1.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float partner = __shfl_xor_sync(0xffffffffu, v[c][j], lane_xor);
-        if (idx < D8) v[c][j] = bfr(bfr(v[c][j] * cf[j]) + bfr(sign * partner * sf[j]));
+      uint4 pw;   // partner group: x[i + hd/2] for the first half of the head, x[i - hd/2] for the second
+      pw.x = __shfl_xor_sync(0xffffffffu, pk[c].x, lane_xor);
+      pw.y = __shfl_xor_sync(0xffffffffu, pk[c].y, lane_xor);
+      pw.z = __shfl_xor_sync(0xffffffffu, pk[c].z, lane_xor);
+      pw.w = __shfl_xor_sync(0xffffffffu, pk[c].w, lane_xor);
+      if (idx < D8) {
+        // bf(bf(x*cos) + bf(rotate_half(x)*sin)), rotate_half = [-x2, x1]  (esme/rotary.py:17-43)
+        if (o < half) {
+          pk[c].x = bsub2(bmul2(pk[c].x, cw.x), bmul2(pw.x, sw.x));
+          pk[c].y = bsub2(bmul2(pk[c].y, cw.y), bmul2(pw.y, sw.y));
+          pk[c].z = bsub2(bmul2(pk[c].z, cw.z), bmul2(pw.z, sw.z));
+          pk[c].w = bsub2(bmul2(pk[c].w, cw.w), bmul2(pw.w, sw.w));
+        } else {
+          pk[c].x = badd2(bmul2(pk[c].x, cw.x), bmul2(pw.x, sw.x));
+          pk[c].y = badd2(bmul2(pk[c].y, cw.y), bmul2(pw.y, sw.y));
+          pk[c].z = badd2(bmul2(pk[c].z, cw.z), bmul2(pw.z, sw.z));
+          pk[c].w = badd2(bmul2(pk[c].w, cw.w), bmul2(pw.w, sw.w));
+        }
       }
     }
   }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     int idx = c * 32 + lane;
-    if (idx < D8) xr[idx] = pack8(v[c]);
+    if (idx < D8) xr[idx] = pk[c];
   }
 }
 
