@@ -63,6 +63,10 @@ int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* 
                      esmk_stream_t s) {
   GUARD(esmk::attn_varlen(q, k, v, ld, out, ldo, cu_lens, tile_info, B, T, H, head_dim, max_len, impl, ST(s)));
 }
+int esmk_attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void* out, const int32_t* cu_lens,
+                   int B, int C, int H, int head_dim, esmk_stream_t s) {
+  GUARD(esmk::attn_pool(q, ldq, k, v, ld, out, cu_lens, B, C, H, head_dim, ST(s)));
+}
 int esmk_quantize(const void* W, int N, int K, int bits, void* data, float* scale, esmk_stream_t s) {
   GUARD(esmk::quantize(W, N, K, bits, data, scale, ST(s)));
 }

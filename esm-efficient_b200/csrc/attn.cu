@@ -563,7 +563,93 @@ attn_generic_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Attention pooling (esme/pooling.py:72-136): C class-token queries attend to all tokens of each sequence
+// (the reference calls flash_attn_varlen_func with max_seqlen_q = 1).  One warp per (sequence, class token,
+// head); same arithmetic as attn_generic_kernel.  out[s, c, :] bf16, [B, C, H*hd].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+attn_pool_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k,
+                 const __nv_bfloat16* __restrict__ v, int ld, __nv_bfloat16* __restrict__ out,
+                 const int32_t* __restrict__ cu_lens, int B, int C, int hd, float scale_log2) {
+  __shared__ float sq[GEN_WARPS][128];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * GEN_WARPS + w;          // (sequence, class token)
+  const int head = blockIdx.y;
+  if (item >= B * C) return;
+  const int seq = item / C, c = item % C;
+  const int s0 = cu_lens[seq], L = cu_lens[seq + 1] - s0;
+  const __nv_bfloat16* qrow = q + (size_t)c * ldq + head * hd;
+  for (int d = lane; d < hd; d += 32) sq[w][d] = __bfloat162float(qrow[d]);
+  __syncwarp();
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < L; j0 += 32) {
+    const int j = j0 + lane;
+    float sc = -INFINITY;
+    if (j < L) {
+      const uint4* kr = reinterpret_cast<const uint4*>(k + (size_t)(s0 + j) * ld + head * hd);
+      float dot = 0.f;
+      for (int cc = 0; cc < hd / 8; ++cc) {
+        const uint4 u = __ldg(kr + cc);
+        const float* qq = &sq[w][cc * 8];
+        dot += qq[0] * bf16_lo(u.x) + qq[1] * bf16_hi(u.x) + qq[2] * bf16_lo(u.y) + qq[3] * bf16_hi(u.y) +
+               qq[4] * bf16_lo(u.z) + qq[5] * bf16_hi(u.z) + qq[6] * bf16_lo(u.w) + qq[7] * bf16_hi(u.w);
+      }
+      sc = dot * scale_log2;
+    }
+    float mx = sc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f(m_run - m_new);
+    const float p = (j < L) ? exp2f(sc - m_new) : 0.f;
+    float ps = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    l_run = l_run * alpha + ps;
+    m_run = m_new;
+    const float pb = bfr(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] *= alpha;
+    const int nk = min(32, L - j0);
+    for (int jj = 0; jj < nk; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, pb, jj);
+      const __nv_bfloat16* vr = v + (size_t)(s0 + j0 + jj) * ld + head * hd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        if (d < hd) acc[i] += pj * __bfloat162float(vr[d]);
+      }
+    }
+  }
+  __nv_bfloat16* orow = out + ((size_t)seq * C + c) * (gridDim.y * hd) + head * hd;
+  const float inv = 1.0f / l_run;          // empty sequence -> NaN, like a softmax over nothing
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < hd) orow[d] = __float2bfloat16_rn(acc[i] * inv);
+  }
+}
+
 }  // namespace
+
+int attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void* out, const int32_t* cu_lens, int B,
+              int C, int H, int hd, cudaStream_t st) {
+  ESMK_REQUIRE(q && k && v && out && cu_lens, "null argument");
+  ESMK_REQUIRE(B >= 1 && C >= 1 && H >= 1, "empty pooling problem");
+  ESMK_REQUIRE(hd % 8 == 0 && hd <= 128, "head_dim must be a multiple of 8 and <= 128");
+  ESMK_REQUIRE(ld % 8 == 0, "k/v pitch must be a multiple of 8");
+  const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
+  dim3 grid((B * C + GEN_WARPS - 1) / GEN_WARPS, H);
+  attn_pool_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k,
+                                                    (const __nv_bfloat16*)v, ld, (__nv_bfloat16*)out, cu_lens, B, C, hd,
+                                                    scale_log2);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
                 const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st) {

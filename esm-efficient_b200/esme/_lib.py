@@ -85,6 +85,8 @@ SIGNATURES = {
     'esmk_mean_pool': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     'esmk_softmax': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_gemm': (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    'esmk_attn_pool': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                             c_void_p]),
     'esmk_quantize': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_dequantize': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'esmk_attn_varlen': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,

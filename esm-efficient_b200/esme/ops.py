@@ -200,3 +200,18 @@ def dequantize(data: torch.Tensor, scale: torch.Tensor, N: int, K: int, bits: in
     L.check(L.lib.esmk_dequantize(data.data_ptr(), scale.data_ptr(), N, K, bits, w.data_ptr(), _stream()),
             'esmk_dequantize')
     return w
+
+
+def attn_pool(cls: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """Class-token attention pooling (esme/pooling.py:72-136): cls [C, D], k / v [T, D] -> [B, C, D]."""
+    _need_cuda(cls, k, v, cu_lens)
+    assert cls.dtype == bf16 and k.dtype == bf16 and v.dtype == bf16 and cu_lens.dtype == torch.int32
+    assert k.shape == v.shape and k.stride(-1) == 1 and v.stride(-1) == 1 and k.stride(0) == v.stride(0)
+    cls = cls.contiguous()
+    C_, D = cls.shape
+    B = cu_lens.numel() - 1
+    out = torch.empty(B, C_, D, dtype=bf16, device=k.device)
+    L.check(L.lib.esmk_attn_pool(cls.data_ptr(), D, k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+                                 cu_lens.contiguous().data_ptr(), B, C_, num_heads, D // num_heads, _stream()),
+            'esmk_attn_pool')
+    return out

@@ -131,6 +131,13 @@ ESMK_API int esmk_attn_varlen(const void* q, const void* k, const void* v, int l
                      const int32_t* cu_lens, const int32_t* tile_info, int B, int T, int H, int head_dim,
                      int max_len, int impl, esmk_stream_t stream);
 
+/* Attention pooling, esme/pooling.py:72-136 (`AttentionPool.forward`, which calls flash_attn_varlen_func with one
+ * query per (class token, sequence), max_seqlen_q = 1): out[s, c, :] = softmax(q_c K_s^T * hd^-0.5) V_s per head.
+ *   q   : bf16 [C, H*hd] class tokens, pitch ldq          k, v : bf16 [T, H*hd] (k already projected), pitch ld
+ *   out : bf16 [B, C, H*hd] dense.  Same arithmetic as esmk_attn_varlen (fp32 softmax, P rounded to bf16). */
+ESMK_API int esmk_attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void* out,
+                            const int32_t* cu_lens, int B, int C, int H, int head_dim, esmk_stream_t stream);
+
 /* ---- weight-only quantised storage --------------------------------------- */
 /* Replaces the bitsandbytes modules the reference's quantised loaders install for q, k, v, out and the two
  * FFN linears (esme/esm.py:414-472 `_load_linear4bit` / `_load_linear8bit` / `_load_quantize`, ESMC :916-946).

@@ -221,6 +221,25 @@ def varlen_attention(q, k, v, cu_lens, p: _Prec):
     return p.r(out)
 
 
+def attention_pool(cls, embed, k_weight, k_bias, cu_lens, num_heads: int, p: _Prec):
+    """esme/pooling.py:72-136 `AttentionPool.forward`: class tokens [C,D] attend to the tokens of every sequence;
+    keys = k(embed), values = embed; flash-attn semantics as in `varlen_attention`.  -> [B, C, D]."""
+    C, D = cls.shape
+    hd = D // num_heads
+    k = _linear(embed, k_weight, k_bias, p)
+    cu = cu_lens.tolist()
+    out = torch.empty(len(cu) - 1, C, D, dtype=p.dt)
+    q = cls.to(p.dt).reshape(C, num_heads, hd).transpose(0, 1)                   # [H,C,hd]
+    for s, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
+        ks = k[a:b].reshape(b - a, num_heads, hd).transpose(0, 1)                # [H,L,hd]
+        vs = embed[a:b].to(p.dt).reshape(b - a, num_heads, hd).transpose(0, 1)
+        sc = torch.matmul(q, ks.transpose(1, 2)) * hd ** -0.5
+        e = torch.exp(sc - sc.max(-1, keepdim=True).values)
+        o = torch.matmul(p.r(e), vs) / e.sum(-1, keepdim=True)                   # [H,C,hd]
+        out[s] = o.transpose(0, 1).reshape(C, D)
+    return p.r(out)
+
+
 # --------------------------------------------------------------------------
 # the forward pass
 # --------------------------------------------------------------------------

@@ -1,0 +1,100 @@
+"""Edge cases of the packed forward on the GPU (the reference's tests cover ragged and padded inputs, single
+sequences and long proteins: tests/test_esm.py, tests/test_attention.py:228-250; its benchmark goes to 3,500
+residues, workflow/inference/inference_on_human.py:12): shapes the tile scheduler, the trimmed last key block and
+the TMA-store epilogue must survive, each checked against the bf16 oracle or an invariance the domain offers."""
+import pytest
+import torch
+
+import esme
+from conftest import GOLDEN, err_stats
+from esme import synthetic
+from oracle import esm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _tiny(family='esm2', layers=2, D=256, H=4, seed=5):
+    sd = synthetic.synthetic_state_dict(family, layers, D, seed=seed)
+    cls = esme.ESMC if family == 'esmc' else esme.ESM2
+    model = cls(layers, D, H)
+    model.load_state_dict(sd, strict=True)
+    return model.to(DEV).eval(), O.OracleConfig(family, layers, D, H), {k: v.clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize('lens', [[3], [129], [128, 128], [2, 2, 2, 2, 2], [127, 1 + 128, 3, 257, 64, 65]])
+def test_ragged_shapes_against_oracle(lens):
+    model, cfg, W = _tiny()
+    tokens, cu, max_len = synthetic.synthetic_batch([max(l, 3) for l in lens], seed=sum(lens))
+    got = model(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    exact = O.forward_packed(cfg, W, tokens, cu, max_len, 'fp64').float()
+    want = O.forward_packed(cfg, W, tokens, cu, max_len, 'bf16').float()
+    _, rms_new, cos_new, _ = err_stats(got, exact)
+    _, rms_orc, _, _ = err_stats(want, exact)
+    assert torch.isfinite(got).all()
+    assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new >= 0.9999
+
+
+def test_longest_benchmark_protein_is_batch_invariant():
+    """One 3,500-residue protein (28 key blocks per query tile) packed between short ones: same logits as alone."""
+    model, cfg, W = _tiny(H=4, D=256)
+    lens = [40, 3502, 77]
+    tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=1)
+    full = model(tokens.to(DEV), (cu.to(DEV), max_len))
+    alone = model(tokens[40:3542].contiguous().to(DEV), (torch.tensor([0, 3502], dtype=torch.int32, device=DEV), 3502))
+    assert torch.isfinite(full.float()).all()
+    assert torch.equal(full[40:3542], alone)
+
+
+def test_many_short_sequences():
+    """1,000 sequences of 5-40 tokens: more work-list records than 128-row tiles of packed tokens."""
+    model, cfg, W = _tiny()
+    g = torch.Generator().manual_seed(2)
+    lens = torch.randint(5, 41, (1000,), generator=g).tolist()
+    tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=4)
+    got = model(tokens.to(DEV), (cu.to(DEV), max_len))
+    assert torch.isfinite(got.float()).all()
+    pick = [0, 1, 500, 999]
+    for s in pick:
+        a, b = int(cu[s]), int(cu[s + 1])
+        alone = model(tokens[a:b].contiguous().to(DEV), (torch.tensor([0, b - a], dtype=torch.int32, device=DEV), b - a))
+        assert torch.equal(got[a:b], alone), s
+
+
+def test_forward_is_cuda_graph_capturable_and_stream_ordered():
+    """esmk_forward is a fixed launch sequence with no host synchronisation: it can be captured into a CUDA graph
+    (the reference's forward cannot: rotary.py:5-14 synchronises twice per layer) and replayed on new inputs."""
+    model = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors', device=DEV)
+    lens = [200, 131, 515]
+    tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=8)
+    tokens, cu = tokens.to(DEV), cu.to(DEV)
+    eager = model(tokens, (cu, max_len))
+    static_tokens = tokens.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        model(static_tokens, (cu, max_len))                        # warm-up on the capture stream (workspace allocation)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = model(static_tokens, (cu, max_len))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager)
+    other, _, _ = synthetic.synthetic_batch(lens, seed=9)
+    static_tokens.copy_(other.to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, model(other.to(DEV), (cu, max_len)))
+    assert not torch.equal(static_out, eager)
+
+
+def test_esmc_ragged_against_oracle():
+    model, cfg, W = _tiny('esmc', layers=2, D=192, H=3, seed=6)
+    tokens, cu, max_len = synthetic.synthetic_batch([130, 3, 64, 300], seed=12)
+    got = model.predict_log_prob(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    exact = O.log_softmax(O.forward_packed(cfg, W, tokens, cu, max_len, 'fp64'), 'fp64').float()
+    want = O.log_softmax(O.forward_packed(cfg, W, tokens, cu, max_len, 'bf16'), 'bf16').float()
+    _, rms_new, cos_new, _ = err_stats(got, exact)
+    _, rms_orc, _, _ = err_stats(want, exact)
+    assert rms_new <= 1.5 * rms_orc + 1e-3 and cos_new >= 0.9999

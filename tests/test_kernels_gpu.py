@@ -115,3 +115,34 @@ def test_partition_mean_pool():
     x320 = torch.randn(10, 320, generator=g).bfloat16()
     got = partition_mean_pool(x320.cuda(), torch.tensor([0, 4, 10], dtype=torch.int32).cuda())
     assert (got.float().cpu()[1] - x320[4:].float().mean(0)).abs().max() <= 4e-3
+
+
+def test_attention_pool_heads_match_reference():
+    """esme.pooling.AttentionPool / LearnedAggregation / BinaryLearnedAggregation (one esmk_attn_pool launch) vs the
+    real reference's outputs (tests/golden/attn_pool.npz) and the oracle (reference: esme/pooling.py:72-228)."""
+    from conftest import err_stats, load_golden
+    from esme import pooling
+    from oracle import esm_oracle as O
+    g = load_golden('attn_pool.npz')
+    H, cu, max_len = int(g['heads']), g['cu_lens'].cuda(), int(g['max_len'])
+    embed = g['embed'].bfloat16().cuda()
+    pool = pooling.AttentionPool(H, embed.shape[1]).cuda()
+    with torch.no_grad():
+        pool.k.weight.copy_(g['pool.k.weight'])
+        pool.k.bias.copy_(g['pool.k.bias'])
+    got = pool(g['cls'].bfloat16().cuda(), embed, (cu, max_len))
+    assert got.shape == g['pooled'].shape and got.dtype == torch.bfloat16
+    want = O.attention_pool(g['cls'], g['embed'], g['pool.k.weight'], g['pool.k.bias'], g['cu_lens'], H, O._Prec('bf16'))
+    # (P is rounded to bf16 per 32-key chunk against the running maximum here, per row against the global maximum in
+    #  the oracle: equivalent roundings, not identical ones -- same bound as test_attention_generic_kernel)
+    assert (got.float().cpu() != want.float()).float().mean() < 0.35
+    assert (got.float().cpu() - want.float()).abs().max() <= 8e-3 * want.abs().max()
+    _, rms, cos, _ = err_stats(got.float().cpu(), g['pooled'])
+    assert rms < 3e-3 and cos > 0.9999
+    for prefix, cls_, key, args in (('agg.', pooling.LearnedAggregation, 'aggregated', (3, H, embed.shape[1])),
+                                    ('bin.', pooling.BinaryLearnedAggregation, 'binary', (H, embed.shape[1]))):
+        head = cls_(*args).cuda()
+        head.load_state_dict({k[len(prefix):]: v.bfloat16() for k, v in g.items() if k.startswith(prefix)}, strict=True)
+        y = head(embed, (cu, max_len))
+        assert y.shape == g[key].shape
+        assert (y.float().cpu() - g[key]).abs().max() <= 0.02 * g[key].abs().max() + 0.02
