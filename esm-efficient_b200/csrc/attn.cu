@@ -158,6 +158,8 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
               const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
               long long* __restrict__ trace, long long* __restrict__ cta_trace) {
+  griddep_launch_dependents();   // the next kernel (out-projection) may be scheduled as SMs drain
+  griddep_wait();                // tile_info / q / k / v of the previous kernels are visible from here
   const long long t_entry = cta_trace ? (long long)global_timer_ns() : 0;
   // work item: {first packed row of the sequence, sequence length, first query row of this tile, -}
   // grid = (head groups, tiles): launch order walks all head groups of the longest sequences first (global LPT)
@@ -701,9 +703,8 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       ESMK_CUDA(cudaMalloc(&trace, trace_n * sizeof(long long)));
       ESMK_CUDA(cudaMemsetAsync(trace, 0, trace_n * sizeof(long long), st));
     }
-    kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, (__nv_bfloat16*)out, ldo,
-                                                      reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2,
-                                                      trace, cta_trace);
+    ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
+                         reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2, trace, cta_trace));
     if (cta_trace != nullptr) {   // debugging aid only
       std::vector<long long> host(cta_n);
       ESMK_CUDA(cudaStreamSynchronize(st));

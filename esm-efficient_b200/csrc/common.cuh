@@ -39,8 +39,27 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
 int sm_count();
+// Programmatic dependent launch (ESMK_PDL=0 disables): kernels launched with this attribute may be scheduled while
+// the previous kernel on the stream is still draining; they call griddep_wait() before touching global memory.
+bool pdl_enabled();
 
 #ifdef __CUDACC__
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute (see pdl_enabled)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------
 // bf16 helpers.  bfr(x) = value of x after a round-to-nearest-even trip through
 // bf16: the reference materialises a bf16 tensor after every op, the fused
@@ -104,6 +123,15 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ----------------------------------------------------------------------------
+// programmatic dependent launch: griddep_launch_dependents() lets the NEXT kernel on the stream be scheduled as
+// SM resources free up (its prologue and launch latency overlap this kernel's tail); griddep_wait() blocks until
+// every prerequisite grid has completed and its memory operations are visible.  Both are no-ops for kernels
+// launched without the attribute.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------
 // mbarrier

@@ -218,6 +218,7 @@ template <int EPI, int HD, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiParams ep) {
+  griddep_launch_dependents();   // the next kernel's launch + prologue may overlap this kernel's tail
   constexpr int EPI_WARPS = epi_warps(EPI);
   constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
   constexpr int BSTAGE = PAIR ? B_STAGE / 2 : B_STAGE;
@@ -271,6 +272,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                // barriers / TMEM are set up; operands of the previous kernel are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of W) ===============
@@ -765,19 +767,26 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   const int tile_m = PAIR ? 2 * BM : BM;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
   if (PAIR) {
     const int pairs = sm_count() / 2;
     cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
   } else {
     cfg.gridDim = dim3(tiles < sm_count() ? tiles : sm_count());
   }
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
   cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;

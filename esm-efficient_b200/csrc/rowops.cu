@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, int ldy, int T, int D,
                  float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -225,7 +227,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat
 template <int NCH>
 static void launch_ln(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
                       cudaStream_t st) {
-  layernorm_kernel<NCH><<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+  launch_pdl(layernorm_kernel<NCH>, dim3((T + kRowWarps - 1) / kRowWarps), dim3(kRowWarps * 32), 0, st,
       (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, T, D,
       eps);
 }

@@ -1,5 +1,7 @@
 // Host utilities: thread-local error string, TMA tensor-map encoding through the
 // driver entry point (no link-time libcuda dependency), device properties.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <mutex>
@@ -61,6 +63,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled", "CUresult " + std::to_string((int)r));
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ESMK_PDL"); return e == nullptr || e[0] != '0'; }();
+  return on;
 }
 
 int sm_count() {
