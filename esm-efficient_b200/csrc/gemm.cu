@@ -50,6 +50,7 @@ struct EpiParams {
   const __nv_bfloat16* R;
   int ldr;
   float scale;  // residue_scaling (divisor)
+  float inv_scale;  // RN(1 / scale), see div_scale
   const __nv_bfloat16* cosb;
   const __nv_bfloat16* sinb;
   const int32_t* pos;
@@ -112,6 +113,14 @@ __device__ __forceinline__ void rope64(float (&v)[64], const __nv_bfloat16* __re
       }
     }
   }
+}
+
+// y / s as the reference computes it (true division, esme/attention.py:253-255) without the IEEE-division slow
+// path: one reciprocal multiply and one FMA-exact residual correction give the correctly rounded fp32 quotient
+// except in measure-zero hard cases, and the quotient is rounded to bf16 right after.
+__device__ __forceinline__ float div_scale(float y, float s, float inv) {
+  const float q = y * inv;
+  return fmaf(fmaf(-q, s, y), inv, q);
 }
 
 __device__ __forceinline__ uint4 pack_u4(const float* f) {
@@ -435,7 +444,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const uint32_t y = pack_bf16(bf16_lo(w[4 * j + q]) / ep.scale, bf16_hi(w[4 * j + q]) / ep.scale);
+                  const uint32_t y = pack_bf16(div_scale(bf16_lo(w[4 * j + q]), ep.scale, ep.inv_scale),
+                                             div_scale(bf16_hi(w[4 * j + q]), ep.scale, ep.inv_scale));
                   w[4 * j + q] = badd2(rw[q], y);
                 }
               }
@@ -473,7 +483,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               y = bfr(y);
               if constexpr (EPI == ESMK_EPI_BIAS_GELU) y = gelu_fast(y);
               if constexpr (EPI == ESMK_EPI_RESIDUAL)
-                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(y / ep.scale);
+                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(div_scale(y, ep.scale, ep.inv_scale));
               dst[j] = __float2bfloat16_rn(y);
             }
           }
@@ -714,7 +724,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               unpack_u4(rq[j], r);
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float y = inv_is_one ? v[8 * j + q] : bfr(v[8 * j + q] / ep.scale);
+                const float y = inv_is_one ? v[8 * j + q] : bfr(div_scale(v[8 * j + q], ep.scale, ep.inv_scale));
                 v[8 * j + q] = r[q] + y;
               }
             }
@@ -728,7 +738,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (col0 + j < N) {
               float y = v[j];
               if constexpr (EPI == ESMK_EPI_RESIDUAL)
-                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(y / ep.scale);
+                y = __bfloat162float(ep.R[(size_t)row * ep.ldr + col0 + j]) + bfr(div_scale(y, ep.scale, ep.inv_scale));
               dst[j] = __float2bfloat16_rn(y);
             }
           }
@@ -812,6 +822,7 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   ep.R = (const __nv_bfloat16*)a.R;
   ep.ldr = a.ldr;
   ep.scale = a.residue_scaling;
+  ep.inv_scale = a.residue_scaling != 0.f ? 1.0f / a.residue_scaling : 0.f;
   ep.cosb = (const __nv_bfloat16*)a.rope_cos;
   ep.sinb = (const __nv_bfloat16*)a.rope_sin;
   ep.pos = a.pos;
