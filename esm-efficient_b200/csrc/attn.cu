@@ -152,6 +152,12 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&s)[32], int kv_valid
   } while (0)
 #endif
 
+#ifdef ESMK_ATTN_RELEASE_ARRIVE      // A/B switch: default .release arrivals
+#define ARRIVE(bar) mbar_arrive(bar)
+#else
+#define ARRIVE(bar) mbar_arrive_relaxed(bar)
+#endif
+
 template <int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -354,7 +360,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         TRACE_STAMP(2);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);             // all 4 warps arrived -> S may be overwritten
+        if (lane == 0) ARRIVE(s_free);             // all 4 warps arrived -> S may be overwritten
         bool o_waited = false;
         if (rows_ok) {
           float mine;
@@ -440,7 +446,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         TRACE_STAMP(6);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) ARRIVE(p_full);
       }
       it += n_kv;
       // ---- head epilogue: O / l for this thread's row ----
@@ -453,7 +459,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);                // the next head's first P.V may overwrite O
+      if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
       if (rows_ok && q0 + r < L) {
         __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64;
 #pragma unroll
