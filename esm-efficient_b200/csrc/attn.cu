@@ -672,15 +672,14 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
-    // share of the exponentials evaluated on the FMA pipes (eighths); ESMK_ATTN_POLY overrides (A/B measurements)
+    // share of the exponentials evaluated on the FMA pipes (eighths); ESMK_ATTN_POLY=1 selects the 3/8 variant (A/B measurements)
     using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
                               long long*, long long*);
     static kernel_t kernel = nullptr;
     if (kernel == nullptr) {
       int poly = kDefaultPoly;
       if (const char* e = getenv("ESMK_ATTN_POLY")) poly = atoi(e);
-      kernel_t k = poly <= 0 ? attn64_kernel<0> : poly == 1 ? attn64_kernel<1> : poly == 2 ? attn64_kernel<2>
-                   : poly == 3 ? attn64_kernel<3> : poly == 4 ? attn64_kernel<4> : attn64_kernel<5>;
+      kernel_t k = poly <= 0 ? attn64_kernel<0> : attn64_kernel<3>;   // 3/8 of the exponentials on the FMA pipes
       ESMK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
       kernel = k;
     }
