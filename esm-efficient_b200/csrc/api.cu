@@ -51,6 +51,9 @@ int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_dim, cons
 int esmk_mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo, esmk_stream_t s) {
   GUARD(esmk::mean_pool(x, ldx, cu_lens, B, D, out, ldo, ST(s)));
 }
+int esmk_residual_add(const void* x, const void* y, void* out, long n, float residue_scaling, esmk_stream_t s) {
+  GUARD(esmk::residual_add(x, y, out, n, residue_scaling, ST(s)));
+}
 int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t s) {
   GUARD(esmk::softmax(logits, ld_in, out, ld_out, T, V, log, ST(s)));
 }

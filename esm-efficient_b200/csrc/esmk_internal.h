@@ -23,6 +23,7 @@ int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int
 int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,
                  const void* sinb, const int32_t* pos, cudaStream_t st);
 int mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo, cudaStream_t st);
+int residual_add(const void* x, const void* y, void* out, long n, float scale, cudaStream_t st);
 int softmax(const void* x, int ldx, void* y, int ldy, int T, int V, int log_mode, cudaStream_t st);
 
 int gemm(const esmk_gemm_args& a, cudaStream_t st);

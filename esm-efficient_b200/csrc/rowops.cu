@@ -465,6 +465,37 @@ int mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void
 }
 
 // ---------------------------------------------------------------------------
+// out = bf(x + bf(y / s))  (esme/attention.py:253-255 as stand-alone elementwise ops; the model path fuses this
+// into the GEMM epilogue -- used when LoRA adapters sit between the projection and the residual add)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+residual_add_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* __restrict__ out, long n8, float s,
+                    float inv) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float a[8], b[8];
+  unpack8(x[i], a);
+  unpack8(y[i], b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float q = b[j] * inv;
+    a[j] += bfr(fmaf(fmaf(-q, s, b[j]), inv, q));   // correctly rounded b / s (see div_scale in gemm.cu)
+  }
+  out[i] = pack8(a);
+}
+
+int residual_add(const void* x, const void* y, void* out, long n, float scale, cudaStream_t st) {
+  ESMK_REQUIRE(x && y && out && n >= 0 && n % 8 == 0 && scale != 0.f, "residual_add: n must be a multiple of 8, scale non-zero");
+  if (n == 0) return 0;
+  const long n8 = n / 8;
+  residual_add_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const uint4*)x, (const uint4*)y, (uint4*)out, n8, scale,
+                                                                    1.0f / scale);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // (log-)softmax over a short last dim (V <= 128): one warp per row
 // ---------------------------------------------------------------------------
 __global__ void softmax_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,

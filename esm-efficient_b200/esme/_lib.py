@@ -83,6 +83,7 @@ SIGNATURES = {
     'esmk_qk_norm_rope': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     'esmk_mean_pool': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'esmk_residual_add': (c_int, [c_void_p, c_void_p, c_void_p, C.c_long, c_float, c_void_p]),
     'esmk_softmax': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_gemm': (c_int, [C.POINTER(GemmArgs), c_void_p]),
     'esmk_attn_pool': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

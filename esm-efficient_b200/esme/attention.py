@@ -21,10 +21,19 @@ from .quantization import dense_weight
 from .rotary import RotaryEmbedding
 
 
-def _reject_lora(lora_names):
-    if lora_names is not None:
-        raise NotImplementedError('LoRA adapters are outside the inference hot path of this build; '
-                                  'merge B@A*scaling into the base weights before loading')
+def _base(linear):
+    """The wrapped linear of a LoRA module, or the module itself."""
+    from .lora import LoRA
+    return linear.layer if isinstance(linear, LoRA) else linear
+
+
+def _adapters(linear, x, y, lora_names):
+    """y += the LoRA adapters of `linear` (if it is wrapped) applied to x, in place (esme/attention.py:94-101,
+    136-139: lora_names = None selects every adapter, as LoRA.forward does)."""
+    from .lora import LoRA
+    if isinstance(linear, LoRA):
+        linear.add_adapters_(x, y, lora_names)
+    return y
 
 
 class SwiGLU(nn.Module):
@@ -80,13 +89,18 @@ class FlashMultiheadAttention(nn.Module):
 
     def packed_qkv(self):
         """Concatenated [3D,D] weight and [3D] bias (or None) for the single QKV GEMM."""
-        w = torch.cat((dense_weight(self.q), dense_weight(self.k), dense_weight(self.v)), dim=0).contiguous()
+        q, k, v = _base(self.q), _base(self.k), _base(self.v)
+        w = torch.cat((dense_weight(q), dense_weight(k), dense_weight(v)), dim=0).contiguous()
         b = None
-        if self.q.bias is not None:
-            b = torch.cat((self.q.bias, self.k.bias, self.v.bias), dim=0).contiguous()
+        if q.bias is not None:
+            b = torch.cat((q.bias, k.bias, v.bias), dim=0).contiguous()
         return w, b
 
-    def _qkv_rot(self, x: Tensor, cu_lens: Tensor, max_len: int):
+    def _has_qkv_adapters(self) -> bool:
+        from .lora import LoRA
+        return any(isinstance(m, LoRA) for m in (self.q, self.k, self.v))
+
+    def _qkv_rot(self, x: Tensor, cu_lens: Tensor, max_len: int, lora_names=None):
         """-> qkv [T,3D] with q,k already QK-normalised (ESMC) and rotated."""
         D, H, hd = self.embed_dim, self.num_heads, self.head_dim
         T = x.shape[0]
@@ -97,11 +111,16 @@ class FlashMultiheadAttention(nn.Module):
         if self.rot_emb is not None:
             self.rot_emb._update_cos_sin_cache(max_len, device=x.device, dtype=x.dtype)
             cos, sin = self.rot_emb._cos_cached, self.rot_emb._sin_cached
-        fuse = (cos is not None) and (not self.pre_layernorm) and hd in (16, 32, 64) and (2 * D) % 64 == 0
+        adapters = self._has_qkv_adapters()      # LoRA deltas are added BEFORE the rotation: no fused RoPE epilogue
+        fuse = (cos is not None) and (not self.pre_layernorm) and hd in (16, 32, 64) and (2 * D) % 64 == 0 \
+            and not adapters
         if fuse:
             qkv = ops.linear(h, w, b, epilogue=L.EPI_QKV_ROPE, rope=(cos, sin, pos, hd, 2 * D))
         else:
             qkv = ops.linear(h, w, b)
+            if adapters:
+                for i, proj in enumerate((self.q, self.k, self.v)):
+                    _adapters(proj, h, qkv[:, i * D:(i + 1) * D], lora_names)
             if self.pre_layernorm or cos is not None:
                 ops.qk_norm_rope_(qkv[:, :D], qkv[:, D:2 * D], H, hd,
                                   self.layernorm_q.weight if self.pre_layernorm else None,
@@ -115,10 +134,10 @@ class FlashMultiheadAttention(nn.Module):
         return ops.attn_varlen(q, k, v, cu_lens, max_len, tile_info)
 
     def forward(self, x: Tensor, cu_lens, max_len, lora_names=None) -> Tensor:
-        _reject_lora(lora_names)
-        qkv, tile_info = self._qkv_rot(x, cu_lens, max_len)
+        qkv, tile_info = self._qkv_rot(x, cu_lens, max_len, lora_names)
         a = self._attn(qkv, cu_lens, max_len, tile_info)
-        return ops.linear(a, dense_weight(self.out), self.out.bias)
+        out = _base(self.out)
+        return _adapters(self.out, a, ops.linear(a, dense_weight(out), out.bias), lora_names)
 
 
 class FlashTransformerLayer(nn.Module):
@@ -154,12 +173,17 @@ class FlashTransformerLayer(nn.Module):
         return self.final[-1].in_features
 
     def forward(self, x: Tensor, cu_lens, max_len, lora_names=None) -> Tensor:
-        _reject_lora(lora_names)
         sa, s = self.self_attn, float(self.residue_scaling)
-        qkv, tile_info = sa._qkv_rot(x, cu_lens, max_len)
+        qkv, tile_info = sa._qkv_rot(x, cu_lens, max_len, lora_names)
         a = sa._attn(qkv, cu_lens, max_len, tile_info)
-        # x + out(a) / s, fused into the out-projection epilogue
-        x = ops.linear(a, dense_weight(sa.out), sa.out.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
+        out = _base(sa.out)
+        if out is sa.out:
+            # x + out(a) / s, fused into the out-projection epilogue
+            x = ops.linear(a, dense_weight(out), out.bias, epilogue=L.EPI_RESIDUAL, residual=x, residue_scaling=s)
+        else:
+            # with adapters on the output projection the reference's order applies: o = out(a) + adapters, x + o / s
+            o = _adapters(sa.out, a, ops.linear(a, dense_weight(out), out.bias), lora_names)
+            x = ops.residual_add(x, o, s)
         ln = self.final[0]
         h = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
         if self.final_activation == 'gelu':

@@ -17,6 +17,7 @@ from . import ops
 from .alphabet import Alphabet, Alphabet3
 from .attention import FlashTransformerLayer, SwiGLU
 from .head import RobertaLMHead
+from .lora import LoRA, has_lora, lora_state_dict, mark_only_lora_as_trainable
 from .quantization import _QuantLinear, dense_weight, quantize_model_
 
 model_names = ['esm2_8m', 'esm2_35m', 'esm2_150m', 'esm2_650m', 'esm2_3b', 'esm2_15b',
@@ -244,7 +245,7 @@ class ESM2(nn.Module):
             f'Invalid layer indices {layers}. The number of layers in the model is {len(self.layers)}.'
         return layers
 
-    def _packed(self, tokens, pad_args, kind, layers=()):
+    def _packed(self, tokens, pad_args, kind, layers=(), lora_names=None):
         """Run the engine on 1-D tokens or on the packed form of 2-D tokens."""
         if pad_args is not None:
             assert tokens.ndim == 1, 'tokens are expected to be unpadded with shape (batch * seq_len)'
@@ -254,15 +255,42 @@ class ESM2(nn.Module):
             assert tokens.ndim == 2, 'tokens are expected to be padded with shape (batch, seq_len, embed_dim)'
             grid = tuple(tokens.shape)
             tokens, indices, cu_lens, max_len = self._unpad(tokens)
-        eng = self.engine()
         ops._need_cuda(tokens, cu_lens)
         assert tokens.dtype == torch.int64, 'tokens must be int64'
         tokens = tokens.contiguous()
         cu_lens = cu_lens.to(device=tokens.device, dtype=torch.int32).contiguous()
+        if has_lora(self):
+            out, reps = self._layer_loop(tokens, cu_lens, int(max_len), kind, layers, lora_names)
+            return out, reps, indices, grid, (cu_lens, int(max_len))
+        eng = self.engine()
         taps = {i: torch.empty(tokens.numel(), self.embed_dim, dtype=torch.bfloat16, device=tokens.device)
                 for i in layers}
         out = eng.forward(tokens, cu_lens, int(max_len), kind, taps)
         return out, [taps[i] for i in layers], indices, grid, (cu_lens, int(max_len))
+
+    def _layer_loop(self, tokens, cu_lens, max_len, kind, layers, lora_names):
+        """The reference's own layer loop (esme/esm.py:243-252) over the operator-level modules; used when LoRA
+        adapters are attached (they sit between the projections and the fused epilogues of `esmk_forward`)."""
+        x = self.embedding(tokens)
+        reps = []
+        for i, layer in enumerate(self.layers):
+            x = layer(x, cu_lens, max_len, lora_names)
+            if i in layers:
+                reps.append(x)
+        reps = [reps[layers.index(i)] for i in layers] if layers else []
+        fn = self.emb_layer_norm_after
+        x = ops.layernorm(x, fn.weight, fn.bias, fn.eps)
+        if kind == L.OUT_REPRESENTATION:
+            return x, reps
+        return self._lm_head_ops(x, kind), reps
+
+    def _lm_head_ops(self, x, kind):
+        logits = self.lm_head(x)
+        if kind == L.OUT_LOG_PROB:
+            return ops.softmax(logits, log=True)
+        if kind == L.OUT_PROB:
+            return ops.softmax(logits, log=False)
+        return logits
 
     @staticmethod
     def _pad(x, indices, rows):
@@ -275,10 +303,10 @@ class ESM2(nn.Module):
         """esme/esm.py:201-266: final-LayerNorm representations [T,D] (packed) or
         [B,S,D] (padded input / pad_output), optionally concatenated with the raw
         outputs of the intermediate `layers` on the feature dim."""
-        if lora_names is not None:
-            raise NotImplementedError('LoRA adapters are not part of this build')
+        self._check_lora_names(lora_names)
         layers = self._check_layers(layers)
-        x, reps, indices, grid, (cu_lens, max_len) = self._packed(tokens, pad_args, L.OUT_REPRESENTATION, layers)
+        x, reps, indices, grid, (cu_lens, max_len) = self._packed(tokens, pad_args, L.OUT_REPRESENTATION, layers,
+                                                                  lora_names)
         if pad_output or pad_args is None:
             if grid is None:
                 assert pad_indices is not None, 'pad_output=True on packed tokens needs pad_indices'
@@ -291,15 +319,76 @@ class ESM2(nn.Module):
         return x
 
     def _head_output(self, tokens, pad_args, pad_output, pad_indices, lora_names, kind):
-        if lora_names is not None:
-            raise NotImplementedError('LoRA adapters are not part of this build')
+        self._check_lora_names(lora_names)
         if pad_args is not None and not pad_output:
-            return self._packed(tokens, pad_args, kind)[0]
+            return self._packed(tokens, pad_args, kind, lora_names=lora_names)[0]
         # padded output: the reference runs the LM head on every row of the padded grid,
         # pad rows included (esme/esm.py:254-255, 281-282) -> constant lm_head(0) rows
-        z = self.forward_representation(tokens, pad_args, pad_output, pad_indices)
-        out = self.engine().lm_head(z.reshape(-1, z.shape[-1]), kind)
+        z = self.forward_representation(tokens, pad_args, pad_output, pad_indices, lora_names)
+        z2 = z.reshape(-1, z.shape[-1])
+        out = self._lm_head_ops(z2, kind) if has_lora(self) else self.engine().lm_head(z2, kind)
         return out.reshape(*z.shape[:-1], -1)
+
+    def _check_lora_names(self, lora_names):
+        if lora_names is not None and not has_lora(self):
+            raise ValueError('lora_names given but the model carries no LoRA adapters (add_lora / load_lora first)')
+
+    # ---- LoRA plumbing (esme/esm.py:495-616) -------------------------------------
+    def trainable_parameters(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def add_lora(self, rank=16, alpha=16, layers=('query', 'value', 'output'), dropout_p=0., adapter_names=None):
+        _layers = set(layers)
+        assert len(_layers.difference({'query', 'value', 'key', 'output'})) == 0, \
+            'layers must be a subset of {"query", "value", "key", "output"}'
+        self.lora_kwargs = {'rank': rank, 'alpha': alpha, 'dropout_p': dropout_p, 'layers': list(_layers),
+                            'names': adapter_names}
+        targets = [m for key, m in (('query', 'q'), ('value', 'v'), ('key', 'k'), ('output', 'out')) if key in _layers]
+        for layer in self.layers:
+            for j in targets:
+                module = getattr(layer.self_attn, j)
+                if not isinstance(module, LoRA):
+                    setattr(layer.self_attn, j, LoRA(module, rank=rank, alpha=alpha, dropout_p=dropout_p,
+                                                     names=adapter_names))
+        self._engine = None
+        self.mark_only_lora_as_trainable(adapter_names)
+        return self
+
+    def mark_only_lora_as_trainable(self, adapter_names=None):
+        mark_only_lora_as_trainable(self, adapter_names)
+        return self
+
+    def lora_state_dict(self, adapter_names=None):
+        return lora_state_dict(self, adapter_names)
+
+    def save_lora(self, path: str, adapter_names=None):
+        from safetensors.torch import save_file
+        state = self.lora_state_dict(adapter_names)
+        assert len(state) > 0, 'No LoRA adapters found to save'
+        kw = self.lora_kwargs
+        metadata = {'rank': str(kw['rank']), 'alpha': str(kw['alpha']), 'dropout_p': str(kw['dropout_p']),
+                    'layers': ','.join(kw['layers']), 'names': ','.join(adapter_names or kw['names']), 'format': 'pt'}
+        save_file({k: v.contiguous() for k, v in state.items()}, path, metadata)
+        return self
+
+    def load_lora(self, path: str, names=None):
+        with safe_open(path, 'pt') as f:
+            metadata = f.metadata()
+            self.add_lora(rank=int(metadata['rank']), alpha=float(metadata['alpha']),
+                          dropout_p=float(metadata['dropout_p']), layers=metadata['layers'].split(','),
+                          adapter_names=metadata.get('names').split(','))
+            own = dict(self.named_parameters())
+            missing = [k for k in f.keys() if k not in own]
+            assert len(missing) == 0, f'Expected LoRA keys in the model missing state_dict: {missing}'
+            with torch.no_grad():
+                for k in f.keys():
+                    own[k].copy_(f.get_tensor(k))
+        return self
+
+    def mark_lmhead(self, trainable=True):
+        for param in self.lm_head.parameters():
+            param.requires_grad_(trainable)
+        return self
 
     def forward(self, tokens, pad_args=None, pad_output=False, pad_indices=None, lora_names=None):
         """Logits: [T,V] for packed tokens + pad_args=(cu_lens, max_len); [B,S,V] for padded tokens."""

@@ -215,3 +215,14 @@ def attn_pool(cls: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torc
                                  cu_lens.contiguous().data_ptr(), B, C_, num_heads, D // num_heads, _stream()),
             'esmk_attn_pool')
     return out
+
+
+def residual_add(x: torch.Tensor, y: torch.Tensor, residue_scaling: float = 1.0) -> torch.Tensor:
+    """bf(x + bf(y / residue_scaling)) (esme/attention.py:253-255 as stand-alone ops)."""
+    _need_cuda(x, y)
+    assert x.dtype == bf16 and y.dtype == bf16 and x.shape == y.shape and x.numel() % 8 == 0
+    xc, yc = x.contiguous(), y.contiguous()
+    out = torch.empty_like(xc)
+    L.check(L.lib.esmk_residual_add(xc.data_ptr(), yc.data_ptr(), out.data_ptr(), xc.numel(), float(residue_scaling),
+                                    _stream()), 'esmk_residual_add')
+    return out

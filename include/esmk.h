@@ -81,6 +81,11 @@ ESMK_API int esmk_qk_norm_rope(void* q, void* k, int ld, int T, int H, int head_
 ESMK_API int esmk_mean_pool(const void* x, int ldx, const int32_t* cu_lens, int B, int D, void* out, int ldo,
                             esmk_stream_t stream);
 
+/* esme/attention.py:253-255 as stand-alone elementwise ops: out = bf(x + bf(y / residue_scaling)) over n contiguous
+ * bf16 elements (n % 8 == 0; out may alias x).  The model path fuses this into the GEMM epilogue; this entry serves
+ * the LoRA path, where adapters are added between the projection and the residual. */
+ESMK_API int esmk_residual_add(const void* x, const void* y, void* out, long n, float residue_scaling, esmk_stream_t stream);
+
 /* esme/esm.py:297,317: (log_)softmax over the last dim of bf16 logits [T,V], bf16 out. */
 ESMK_API int esmk_softmax(const void* logits, int ld_in, void* out, int ld_out, int T, int V, int log, esmk_stream_t stream);
 
