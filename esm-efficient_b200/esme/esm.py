@@ -255,14 +255,14 @@ class ESM2(nn.Module):
             assert tokens.ndim == 2, 'tokens are expected to be padded with shape (batch, seq_len, embed_dim)'
             grid = tuple(tokens.shape)
             tokens, indices, cu_lens, max_len = self._unpad(tokens)
+        eng = None if has_lora(self) else self.engine()      # (raises for a model that is not on a CUDA device)
         ops._need_cuda(tokens, cu_lens)
         assert tokens.dtype == torch.int64, 'tokens must be int64'
         tokens = tokens.contiguous()
         cu_lens = cu_lens.to(device=tokens.device, dtype=torch.int32).contiguous()
-        if has_lora(self):
+        if eng is None:
             out, reps = self._layer_loop(tokens, cu_lens, int(max_len), kind, layers, lora_names)
             return out, reps, indices, grid, (cu_lens, int(max_len))
-        eng = self.engine()
         taps = {i: torch.empty(tokens.numel(), self.embed_dim, dtype=torch.bfloat16, device=tokens.device)
                 for i in layers}
         out = eng.forward(tokens, cu_lens, int(max_len), kind, taps)
