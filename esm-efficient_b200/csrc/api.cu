@@ -40,6 +40,9 @@ int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D
                const uint8_t* zero_rows, esmk_stream_t s) {
   GUARD(esmk::embed(tokens, table, out, T, D, vocab, zero_token, zero_rows, ST(s)));
 }
+int esmk_add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset, esmk_stream_t s) {
+  GUARD(esmk::add_positions(x, table, pos, T, D, rows, offset, ST(s)));
+}
 int esmk_layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
                    esmk_stream_t s) {
   GUARD(esmk::layernorm(x, ldx, w, b, y, ldy, T, D, eps, ST(s)));

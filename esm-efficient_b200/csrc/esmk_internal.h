@@ -18,6 +18,7 @@ int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile
 int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st);
 int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
           const uint8_t* zero_rows, cudaStream_t st);
+int add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset, cudaStream_t st);
 int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
               cudaStream_t st);
 int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,

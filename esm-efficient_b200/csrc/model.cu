@@ -174,6 +174,8 @@ int model_create(const esmk_config* cfg, const esmk_weights* w, esmk_model** out
   if (cfg->family == 1) ESMK_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, "ESMC head_dim must be 16, 32, 64 or 128");
   ESMK_REQUIRE(cfg->vocab >= 1 && cfg->vocab <= 128 && cfg->embed_rows >= cfg->vocab - 0, "bad vocab");
   ESMK_REQUIRE(cfg->residue_scaling > 0.f, "residue_scaling must be positive");
+  ESMK_REQUIRE((w->pos_embed != nullptr) == (cfg->pos_rows > 0), "pos_embed and pos_rows must be given together");
+  ESMK_REQUIRE(cfg->family == 0 || (!cfg->no_rotary && w->pos_embed == nullptr), "learned positions are an ESM-1b/1v (family 0) feature");
   if (cfg->family == 1) ESMK_REQUIRE(cfg->ffn_dim % 32 == 0, "ESMC ffn_dim must be a multiple of 32");
   ESMK_REQUIRE(w->embed && w->layers && w->final_norm_w && w->head_dense_w && w->head_dense_b && w->head_norm_w &&
                    w->head_norm_b && w->head_final_w && w->head_final_b,
@@ -216,12 +218,17 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
                "workspace too small (see esmk_workspace_bytes)");
   const int D = c.embed_dim, H = c.attention_heads, hd = D / H, F = c.ffn_dim;
   const float s = c.residue_scaling;
-  const bool fused_rope = (c.family == 0) && (hd == 16 || hd == 32 || hd == 64) && ((2 * D) % 64 == 0);
+  const bool fused_rope = (c.family == 0) && !c.no_rotary && (hd == 16 || hd == 32 || hd == 64) && ((2 * D) % 64 == 0);
 
   PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_info, st));
   PROF(ESMK_PROF_MISC, rope_tables(b.cosb, b.sinb, max_len, hd, st));
   // esme/esm.py:188-189: ESM2 zeroes <mask>(32) rows; ESMC (esm.py:876) does not
   PROF(ESMK_PROF_MISC, embed(tokens, m->w.embed, b.x, T, D, c.embed_rows, c.family == 0 ? 32 : -1, zero_rows, st));
+  if (m->w.pos_embed != nullptr) {   // ESM-1b / ESM-1v: learned positions (+ LayerNorm before the layers for 1b)
+    PROF(ESMK_PROF_MISC, add_positions(b.x, m->w.pos_embed, b.pos, T, D, c.pos_rows, 2, st));
+    if (m->w.pre_norm_w != nullptr)
+      PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, m->w.pre_norm_w, m->w.pre_norm_b, b.x, D, T, D, 1e-5f, st));
+  }
 
   for (int i = 0; i < c.num_layers; ++i) {
     const esmk_layer_weights& l = m->layers[i];
@@ -237,7 +244,9 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
       PROF(ESMK_PROF_GEMM_QKV, gemm(g, st));
     } else {
       PROF(ESMK_PROF_GEMM_QKV, linear(b.h, D, wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
-      PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, b.cosb, b.sinb, b.pos, st));
+      if (!c.no_rotary || l.qln_w != nullptr)
+        PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, c.no_rotary ? nullptr : b.cosb,
+                                          c.no_rotary ? nullptr : b.sinb, b.pos, st));
     }
     PROF(ESMK_PROF_ATTENTION,
          attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));

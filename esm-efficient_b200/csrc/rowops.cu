@@ -163,6 +163,32 @@ int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int
   return 0;
 }
 
+// ESM-1b / ESM-1v: x[t] = bf(x[t] + P[pos[t] + offset]) in place (esme/esm.py:634-646, esme/embedding.py:36-92:
+// learned positions count from padding_idx + 1 inside each sequence)
+__global__ void add_positions_kernel(uint4* __restrict__ x, const uint4* __restrict__ table, const int32_t* __restrict__ pos,
+                                     int T, int D8, int rows, int offset) {
+  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const int p = min(max(pos[row] + offset, 0), rows - 1);
+  const uint4* src = table + (size_t)p * D8;
+  uint4* dst = x + (size_t)row * D8;
+  for (int c = lane; c < D8; c += 32) {
+    const uint4 a = dst[c], b = __ldg(src + c);
+    dst[c] = make_uint4(badd2(a.x, b.x), badd2(a.y, b.y), badd2(a.z, b.z), badd2(a.w, b.w));
+  }
+}
+
+int add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset, cudaStream_t st) {
+  ESMK_REQUIRE(x && table && pos && D % 8 == 0 && rows >= 1, "add_positions: bad arguments");
+  if (T == 0) return 0;
+  add_positions_kernel<<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>((uint4*)x, (const uint4*)table, pos, T, D / 8,
+                                                                                 rows, offset);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // LayerNorm.  NCH = uint4 chunks held per lane (row fits in registers for
 // D <= NCH*256); exact two-pass statistics in fp32.

@@ -8,23 +8,7 @@ pass runs in hand-written sm_100a CUDA kernels (libesmk.so, C ABI in
 include/esmk.h).  CUDA-only: there is no CPU or eager fallback.
 """
 from .alphabet import tokenize
-from .esm import ESM, ESM2, ESMC
+from .esm import ESM, ESM1b, ESM1v, ESM2, ESMC
 
-
-def _out_of_scope(name):
-    class _Missing:
-        def __init__(self, *a, **kw):
-            raise NotImplementedError(f'{name} (learned positional embeddings) is outside the hot-path scope '
-                                      f'of this build; see DESIGN.md')
-
-        @classmethod
-        def from_pretrained(cls, *a, **kw):
-            cls()
-    _Missing.__name__ = name
-    return _Missing
-
-
-ESM1b = _out_of_scope('ESM1b')
-ESM1v = _out_of_scope('ESM1v')
 
 __all__ = ['ESM', 'ESMC', 'ESM2', 'ESM1b', 'ESM1v', 'tokenize']

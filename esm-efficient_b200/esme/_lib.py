@@ -42,6 +42,7 @@ class Config(C.Structure):
     _fields_ = [
         ('family', c_int), ('num_layers', c_int), ('embed_dim', c_int), ('attention_heads', c_int),
         ('ffn_dim', c_int), ('vocab', c_int), ('embed_rows', c_int), ('residue_scaling', c_float),
+        ('no_rotary', c_int), ('pos_rows', c_int),
     ]
 
 
@@ -64,6 +65,7 @@ class Weights(C.Structure):
         ('head_dense_w', c_void_p), ('head_dense_b', c_void_p),
         ('head_norm_w', c_void_p), ('head_norm_b', c_void_p),
         ('head_final_w', c_void_p), ('head_final_b', c_void_p),
+        ('pos_embed', c_void_p), ('pre_norm_w', c_void_p), ('pre_norm_b', c_void_p),
     ]
 
 
@@ -79,6 +81,7 @@ SIGNATURES = {
     'esmk_batch_meta': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_rope_tables': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'esmk_embed': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'esmk_add_positions': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_layernorm': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     'esmk_qk_norm_rope': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),

@@ -16,6 +16,7 @@ from . import _lib as L
 from . import ops
 from .alphabet import Alphabet, Alphabet3
 from .attention import FlashTransformerLayer, SwiGLU
+from .embedding import LearnedPositionalEmbedding
 from .head import RobertaLMHead
 from .lora import LoRA, has_lora, lora_state_dict, mark_only_lora_as_trainable
 from .quantization import _QuantLinear, dense_weight, quantize_model_
@@ -44,9 +45,10 @@ class ESM(nn.Module):
             return ESM2.from_pretrained(path, quantization, checkpointing, device)
         if name == 'esmc':
             return ESMC.from_pretrained(path, quantization, checkpointing, device)
-        if name in ('esm1b', 'esm1v'):
-            raise NotImplementedError(f'{name}: learned-positional-embedding models are outside this build '
-                                      f'(SURVEY.md §2: not in the hot-path scope)')
+        if name == 'esm1b':
+            return ESM1b.from_pretrained(path, quantization, checkpointing, device)
+        if name == 'esm1v':
+            return ESM1v.from_pretrained(path, quantization, checkpointing, device)
         raise ValueError(f'Invalid model name: {name}. Must be one of {model_names}')
 
 
@@ -87,9 +89,17 @@ class _Engine:
         w.head_dense_w, w.head_dense_b = hd.dense.weight.data_ptr(), hd.dense.bias.data_ptr()
         w.head_norm_w, w.head_norm_b = hd.layer_norm.weight.data_ptr(), hd.layer_norm.bias.data_ptr()
         w.head_final_w, w.head_final_b = hd.final.weight.data_ptr(), hd.final.bias.data_ptr()
+        pos = getattr(model, 'embed_positions', None)
+        pre = getattr(model, 'emb_layer_norm_before', None)
+        if pos is not None:
+            w.pos_embed = pos.weight.data_ptr()
+        if pre is not None:
+            w.pre_norm_w, w.pre_norm_b = pre.weight.data_ptr(), pre.bias.data_ptr()
         cfg = L.Config(family, model.num_layers, model.embed_dim, model.attention_heads,
                        model.layers[0].ffn_dim, hd.final.out_features, model.embed_tokens.num_embeddings,
-                       float(model.layers[0].residue_scaling))
+                       float(model.layers[0].residue_scaling),
+                       0 if model.layers[0].self_attn.rot_emb is not None else 1,
+                       0 if pos is None else pos.weight.shape[0])
         self.vocab = hd.final.out_features
         self.embed_dim = model.embed_dim
         handle = L.c_void_p()
@@ -181,8 +191,7 @@ class ESM2(nn.Module):
                  checkpointing: bool = False, rotary_embedding: bool = True, dropout: float = 0.,
                  dtype=torch.bfloat16):
         super().__init__()
-        if not rotary_embedding:
-            raise NotImplementedError('ESM2/ESMC always use rotary embeddings')
+        self.rotary_embedding = bool(rotary_embedding)
         self.num_layers = num_layers
         self.embed_dim = embed_dim
         self.attention_heads = attention_heads
@@ -197,7 +206,7 @@ class ESM2(nn.Module):
 
     # ---- architecture hooks (ESMC overrides) --------------------------------
     def _make_layer(self, dropout, dtype):
-        return FlashTransformerLayer(self.embed_dim, 4, self.attention_heads, rotary_embedding=True,
+        return FlashTransformerLayer(self.embed_dim, 4, self.attention_heads, rotary_embedding=self.rotary_embedding,
                                      pre_layernorm=False, bias=True, final_activation='gelu',
                                      dropout=dropout, dtype=dtype)
 
@@ -449,6 +458,67 @@ class ESM2(nn.Module):
             # (this library's formats, see esme/quantization.py); biases, LayerNorms, embedding, LM head stay bf16
             quantize_model_(model, 4 if quantization == '4bit' else 8)
         return model
+
+
+class ESM1b(ESM2):
+    """ESM-1b (reference: esme/esm.py:618-679): the ESM2 block stack without rotary embeddings, a learned
+    positional table and a LayerNorm before the layers.  The reference fixes 33 / 1280 / 20; the optional
+    arguments exist for small test models."""
+
+    _pre_norm = True
+    _max_seq_len = 4096
+
+    def __init__(self, checkpointing: bool = False, dtype=torch.bfloat16, num_layers: int = 33, embed_dim: int = 1280,
+                 attention_heads: int = 20, max_seq_len: Optional[int] = None):
+        super().__init__(num_layers=num_layers, embed_dim=embed_dim, attention_heads=attention_heads,
+                         checkpointing=checkpointing, rotary_embedding=False, dtype=dtype)
+        if self._pre_norm:
+            self.emb_layer_norm_before = nn.LayerNorm(self.embed_dim, dtype=dtype)
+        self.embed_positions = LearnedPositionalEmbedding(max_seq_len or self._max_seq_len, self.embed_dim, dtype=dtype)
+
+    def embedding(self, tokens, pad_args=None):
+        """esme/esm.py:634-656 (ESM-1b) / 696-714 (ESM-1v)."""
+        if tokens.ndim == 2:
+            assert pad_args is None, 'pad_args must be None for esm1b with 2D tokens'
+        elif tokens.ndim == 1:
+            assert pad_args is not None, 'pad_args must be provided for esm1b with 1D tokens'
+        else:
+            raise ValueError('tokens must be 1D or 2D for esm1v')
+        x = ops.embed(tokens, self.embed_tokens.weight, zero_token=self._alphabet.mask_idx)
+        p = self.embed_positions(tokens, pad_args)
+        x = ops.residual_add(x.reshape(-1, x.shape[-1]), p.reshape(-1, p.shape[-1]), 1.0).reshape(x.shape)
+        if self._pre_norm:
+            ln = self.emb_layer_norm_before
+            x = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
+        if tokens.ndim == 2:
+            x = torch.where(~tokens.eq(self._alphabet.padding_idx).unsqueeze(-1), x, torch.zeros_like(x))
+        return x
+
+    def _layer_loop(self, tokens, cu_lens, max_len, kind, layers, lora_names):
+        # (the base class embeds without pad_args; ESM-1b / 1v positions need them)
+        emb = self.embedding
+        self.embedding = lambda t, pad_args=None: emb(t, (cu_lens, max_len))
+        try:
+            return super()._layer_loop(tokens, cu_lens, max_len, kind, layers, lora_names)
+        finally:
+            del self.embedding
+
+    @classmethod
+    def create_model(cls, path, checkpointing=False):
+        """esme/esm.py:677-679 builds the fixed 33 / 1280 / 20 model; dims in the metadata (test fixtures) win."""
+        meta = _read_metadata(path)
+        name = meta['name'].split('_')[0]
+        assert name == cls.__name__.lower(), \
+            f'Invalid weight for the {cls.__name__} model. ' \
+            f'You are trying to load a {name} model weights to a {cls.__name__} model.'
+        kw = {k: int(meta[k]) for k in ('num_layers', 'embed_dim', 'attention_heads', 'max_seq_len') if k in meta}
+        return cls(checkpointing=checkpointing, **kw)
+
+
+class ESM1v(ESM1b):
+    """ESM-1v (reference: esme/esm.py:682-735): ESM-1b without the LayerNorm before the layers."""
+
+    _pre_norm = False
 
 
 class ESMC(ESM2):

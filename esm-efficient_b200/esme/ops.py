@@ -226,3 +226,12 @@ def residual_add(x: torch.Tensor, y: torch.Tensor, residue_scaling: float = 1.0)
     L.check(L.lib.esmk_residual_add(xc.data_ptr(), yc.data_ptr(), out.data_ptr(), xc.numel(), float(residue_scaling),
                                     _stream()), 'esmk_residual_add')
     return out
+
+
+def add_positions_(x: torch.Tensor, table: torch.Tensor, pos: torch.Tensor, offset: int = 2) -> torch.Tensor:
+    """x[t] += table[pos[t] + offset] in place, one bf16 rounding (ESM-1b / ESM-1v learned positions)."""
+    _need_cuda(x, table, pos)
+    assert x.dtype == bf16 and table.dtype == bf16 and pos.dtype == torch.int32 and x.is_contiguous() and table.is_contiguous()
+    L.check(L.lib.esmk_add_positions(x.data_ptr(), table.data_ptr(), pos.data_ptr(), x.shape[0], x.shape[1],
+                                     table.shape[0], offset, _stream()), 'esmk_add_positions')
+    return x

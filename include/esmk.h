@@ -63,6 +63,11 @@ ESMK_API int esmk_rope_tables(void* cos, void* sin, int max_len, int head_dim, e
 ESMK_API int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
                const uint8_t* zero_rows, esmk_stream_t stream);
 
+/* ESM-1b / ESM-1v learned positional embedding, esme/esm.py:634-646 + esme/embedding.py:36-92, in place:
+ * x[t] = bf(x[t] + table[pos[t] + offset]); pos from esmk_batch_meta, offset = padding_idx + 1 = 2, table bf16 [rows, D]. */
+ESMK_API int esmk_add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset,
+                                esmk_stream_t stream);
+
 /* torch.nn.LayerNorm over the last dim (eps, biased variance, fp32 statistics, bf16 in/out):
  * esme/attention.py:92, 222|230; esme/esm.py:252; esme/head.py:26.  bias may be NULL. */
 ESMK_API int esmk_layernorm(const void* x, int ldx, const void* weight, const void* bias, void* y, int ldy, int T, int D,
@@ -167,6 +172,8 @@ typedef struct {
   int family;          /* 0 = ESM2 (bias, GELU FFN, mask-row zeroing), 1 = ESMC (QK-LN, SwiGLU, residue scaling) */
   int num_layers, embed_dim, attention_heads, ffn_dim, vocab, embed_rows;
   float residue_scaling;
+  int no_rotary;       /* 1 = no rotary embedding (ESM-1b / ESM-1v, esme/esm.py:628-629: rotary_embedding=False) */
+  int pos_rows;        /* rows of esmk_weights.pos_embed (0 = none) */
 } esmk_config;
 
 typedef struct {
@@ -190,6 +197,10 @@ typedef struct {
   const void *head_dense_w, *head_dense_b;
   const void *head_norm_w, *head_norm_b;
   const void *head_final_w, *head_final_b; /* [V,D], [V] */
+  /* ESM-1b / ESM-1v (esme/esm.py:618-735): learned positional table [pos_rows, D] added to the token embedding
+   * at row pos + 2; ESM-1b also applies emb_layer_norm_before.  NULL for ESM2 / ESMC. */
+  const void* pos_embed;
+  const void *pre_norm_w, *pre_norm_b;
 } esmk_weights;
 
 typedef struct esmk_model esmk_model_t;

@@ -104,21 +104,30 @@ class OracleConfig:
         return self.embed_dim // self.attention_heads
 
     @property
+    def gelu_family(self) -> bool:
+        """ESM2 block (bias, GELU FFN, mask-row zeroing): esm2 and the rotary-free esm1b / esm1v (esm.py:618-735)."""
+        return self.family in ('esm2', 'esm1b', 'esm1v')
+
+    @property
+    def rotary(self) -> bool:
+        return self.family in ('esm2', 'esmc')
+
+    @property
     def ffn_dim(self) -> int:
-        if self.family == 'esm2':
+        if self.gelu_family:
             return 4 * self.embed_dim                       # esme/esm.py:159
         # esme/attention.py:218-219 with expand 8/3 (esme/esm.py:833)
         return int(((8 / 3 * self.embed_dim) + 255) // 256 * 256)
 
     @property
     def residue_scaling(self) -> float:
-        if self.family == 'esm2':
+        if self.gelu_family:
             return 1.0
         return math.sqrt(self.num_layers / 36)               # esme/esm.py:839
 
     @property
     def vocab(self) -> int:
-        return 33 if self.family == 'esm2' else 64           # esme/esm.py:154,174,828,850
+        return 33 if self.gelu_family else 64                # esme/esm.py:154,174,828,850
 
 
 def config_from_metadata(meta: Dict[str, str]) -> OracleConfig:
@@ -264,8 +273,9 @@ def layer_forward(x, W: Dict[str, torch.Tensor], i: int, cfg: OracleConfig,
         k = p.r(_layer_norm(k, p.w(g('self_attn.layernorm_k.weight')), None))
     T = x.shape[0]
     q, k, v = (t.reshape(T, H, hd) for t in (q, k, v))
-    q = apply_rotary(q, cos, sin, pos, p)
-    k = apply_rotary(k, cos, sin, pos, p)
+    if cfg.rotary:                                            # ESM-1b / 1v: rotary_embedding=False (esm.py:628-629)
+        q = apply_rotary(q, cos, sin, pos, p)
+        k = apply_rotary(k, cos, sin, pos, p)
     a = varlen_attention(q, k, v, cu_lens, p).reshape(T, H * hd)
     o = _linear(a, g('self_attn.out.weight'), g('self_attn.out.bias'), p)
     x = p.r(x + p.r(o / s))
@@ -275,7 +285,7 @@ def layer_forward(x, W: Dict[str, torch.Tensor], i: int, cfg: OracleConfig,
         taps[f'layer{i}.attn'] = a
         taps[f'layer{i}.x_mid'] = x
     gln = p.r(_layer_norm(x, p.w(g('final.0.weight')), p.w(g('final.0.bias'))))
-    if cfg.family == 'esm2':                                  # attention.py:228-236
+    if cfg.gelu_family:                                       # attention.py:228-236
         u = _linear(gln, g('final.1.weight'), g('final.1.bias'), p)
         u = p.r(_gelu(u))
         y = _linear(u, g('final.3.weight'), g('final.3.bias'), p)
@@ -302,11 +312,17 @@ def forward_packed(cfg: OracleConfig, W: Dict[str, torch.Tensor], tokens: torch.
     p = _Prec(mode)
     assert tokens.ndim == 1
     x = p.w(W['embed_tokens.weight'])[tokens]
-    if cfg.family == 'esm2':                                  # esm.py:189 (ESMC: esm.py:876, no zeroing)
+    if cfg.gelu_family:                                       # esm.py:189 (ESMC: esm.py:876, no zeroing)
         x = x.masked_fill((tokens == MASK).unsqueeze(-1), 0.0)
+    pos = positions_from_cu_lens(cu_lens)
+    if not cfg.rotary:
+        # ESM-1b / ESM-1v (esm.py:634-656, 696-714; embedding.py:54-92): learned positions count from
+        # padding_idx + 1 = 2 inside each sequence; ESM-1b then applies emb_layer_norm_before
+        x = p.r(x + p.w(W['embed_positions.weight'])[pos + 2])
+        if 'emb_layer_norm_before.weight' in W:
+            x = p.r(_layer_norm(x, p.w(W['emb_layer_norm_before.weight']), p.w(W['emb_layer_norm_before.bias'])))
     if zero_rows is not None:
         x = x.masked_fill(zero_rows.unsqueeze(-1), 0.0)
-    pos = positions_from_cu_lens(cu_lens)
     cos, sin = rotary_tables(max_len, cfg.head_dim, p)
     for i in range(cfg.num_layers):
         x = layer_forward(x, W, i, cfg, cu_lens, pos, cos, sin, p, taps)

@@ -196,3 +196,34 @@ def test_head_dim_24_model_matches_oracle():
     p = O._Prec('bf16')
     assert torch.equal(qr.float().cpu(), O.apply_rotary(q.float(), cos, sin, pos, p))
     assert torch.equal(kr.float().cpu(), O.apply_rotary(k.float(), cos, sin, pos, p))
+
+
+@pytest.mark.parametrize('name', ['esm1b', 'esm1v'])
+def test_esm1_models_match_reference(name):
+    """ESM-1b / ESM-1v drop-ins (reference esme/esm.py:618-735, esme/embedding.py): engine path, operator-level
+    embedding, padded entry -- against the real reference's outputs on tiny models and the oracle."""
+    g = load_golden(f'{name}_tiny.npz')
+    model = esme.ESM.from_pretrained(f'{GOLDEN}/{name}_tiny.safetensors', device=DEV)
+    assert type(model).__name__ == ('ESM1b' if name == 'esm1b' else 'ESM1v')
+    assert all(layer.self_attn.rot_emb is None for layer in model.layers)
+    tokens, cu, max_len = g['tokens'].to(DEV), g['cu_lens'].to(DEV), g['max_len']
+    cfg, W = O.load_checkpoint(f'{GOLDEN}/{name}_tiny.safetensors')
+    exact = O.forward_packed(cfg, W, g['tokens'], g['cu_lens'], max_len, 'fp64').float()
+    got = model(tokens, (cu, max_len)).float().cpu()
+    _, rms_new, cos_new, agree = err_stats(got, exact)
+    _, rms_ref, cos_ref, agree_ref = err_stats(g['logits'], exact)       # (~1e-2: random weights with a large gain)
+    assert rms_new <= 1.5 * rms_ref + 1e-4 and cos_new >= cos_ref - 2e-4 and agree >= agree_ref - 0.02
+    emb = model.embedding(tokens, (cu, max_len)).float().cpu()
+    assert (emb != g['embedding']).float().mean() < 2e-3                 # gather + add (+ LayerNorm for 1b)
+    rep = model.forward_representation(tokens, (cu, max_len)).float().cpu()
+    assert err_stats(rep, g["representation"])[1] < 3e-2
+    padded = model(esme.tokenize(g['seqs'], Alphabet).to(DEV)).float().cpu()
+    assert padded.shape == g['padded_logits'].shape
+    _, rms, cos, _ = err_stats(padded, g['padded_logits'])
+    assert rms < 1.5 * rms_ref and cos > 0.999
+    with pytest.raises(AssertionError):
+        model.embedding(tokens)                                           # packed tokens need pad_args
+    # mask-margin scoring runs on these models too (ESM-1v is the variant-effect model of the family)
+    from esme.variant import predict_mask_margin
+    df = predict_mask_margin(model, 'MKTAYIAKQRQISFVKSHFSRQLEERLGL', batch_size=8)
+    assert df.shape[0] == 29 * 20 and torch.isfinite(torch.tensor(df['score'].to_numpy())).all()
