@@ -660,11 +660,13 @@ int attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void
 }
 
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
-                const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st) {
+                const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st,
+                int scale_hd) {
   ESMK_REQUIRE(B >= 1 && T >= 1 && H >= 1, "empty attention problem");
   ESMK_REQUIRE(hd % 8 == 0 && hd <= 128, "head_dim must be a multiple of 8 and <= 128");
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
-  const float scale_log2 = (1.0f / sqrtf((float)hd)) * 1.4426950408889634f;
+  // scale_hd: the model's true head_dim when the heads were zero-padded to `hd` (softmax scale = scale_hd^-0.5)
+  const float scale_log2 = (1.0f / sqrtf((float)(scale_hd > 0 ? scale_hd : hd))) * 1.4426950408889634f;
   if (hd == 64 && impl == 0) {
     ESMK_REQUIRE(tile_info != nullptr, "tile_info (esmk_batch_meta) required");
     ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");

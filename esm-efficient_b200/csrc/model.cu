@@ -72,7 +72,7 @@ struct Workspace {
 };
 
 struct Buffers {
-  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb, *wq;
+  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb, *wq, *qkvp, *ap;
   int32_t *pos, *tile_info;
   size_t bytes;
 };
@@ -105,6 +105,10 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len, size_t 
   b.pos = w.take<int32_t>((size_t)T);
   b.tile_info = w.take<int32_t>((size_t)4 * tile_capacity(T, B));
   b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;
+  // small head dims: heads zero-padded to 64 columns for the tcgen05 attention kernel (see pad_heads)
+  const bool pad = hd < 64;
+  b.qkvp = pad ? w.take<__nv_bfloat16>((size_t)T * 3 * c.attention_heads * 64) : nullptr;
+  b.ap = pad ? w.take<__nv_bfloat16>((size_t)T * c.attention_heads * 64) : nullptr;
   b.bytes = w.off;
   return b;
 }
@@ -248,8 +252,16 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
         PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, c.no_rotary ? nullptr : b.cosb,
                                           c.no_rotary ? nullptr : b.sinb, b.pos, st));
     }
-    PROF(ESMK_PROF_ATTENTION,
-         attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));
+    if (hd < 64) {
+      const int Dp = H * 64;
+      PROF(ESMK_PROF_ATTENTION, pad_heads(b.qkv, 3 * D, b.qkvp, T, 3, H, hd, st));
+      PROF(ESMK_PROF_ATTENTION, attn_varlen(b.qkvp, b.qkvp + Dp, b.qkvp + 2 * Dp, 3 * Dp, b.ap, Dp, cu_lens, b.tile_info, B,
+                                            T, H, 64, max_len, 0, st, hd));
+      PROF(ESMK_PROF_ATTENTION, unpad_heads(b.ap, b.a, D, T, H, hd, st));
+    } else {
+      PROF(ESMK_PROF_ATTENTION,
+           attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));
+    }
     ESMK_TRY(weight_of(l.wo, l.q_wo, D, D, b.wq, st, &wo));
     PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
     // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)

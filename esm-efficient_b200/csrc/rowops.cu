@@ -544,6 +544,54 @@ int residual_add(const void* x, const void* y, void* out, long n, float scale, c
 }
 
 // ---------------------------------------------------------------------------
+// Small head dims (ESM2-8M / 35M / 150M: 16 / 24 / 32) run on the head_dim-64 tcgen05 attention kernel with every
+// head zero-padded to 64 columns: zeros add nothing to Q.K^T and produce zero output columns, the softmax scale
+// keeps the true head_dim.  pad: [T, parts*H*hd] (pitch ld_src) -> [T, parts*H*64]; unpad: [T, H*64] -> [T, H*hd].
+// One thread per 16-byte group of the padded row.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pad_heads_kernel(const uint4* __restrict__ src, int ld8, uint4* __restrict__ dst, long n, int heads, int hd8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // (token, part*head, group of 8 inside 64)
+  if (i >= n) return;
+  const int g = (int)(i & 7);
+  const long th = i >> 3;
+  const int h = (int)(th % heads);
+  const long t = th / heads;
+  dst[i] = g < hd8 ? __ldg(src + t * ld8 + (long)h * hd8 + g) : make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256)
+unpad_heads_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ld8, long n, int heads, int hd8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // (token, head, group of 8 inside hd)
+  if (i >= n) return;
+  const int g = (int)(i % hd8);
+  const long th = i / hd8;
+  const int h = (int)(th % heads);
+  const long t = th / heads;
+  dst[t * ld8 + (long)h * hd8 + g] = __ldg(src + (t * heads + h) * 8 + g);
+}
+
+int pad_heads(const void* src, int ld_src, void* dst, int T, int parts, int H, int hd, cudaStream_t st) {
+  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < 64 && ld_src % 8 == 0, "pad_heads: head_dim must be a multiple of 8 below 64");
+  const long n = (long)T * parts * H * 8;
+  if (n == 0) return 0;
+  pad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, ld_src / 8, (uint4*)dst, n, parts * H, hd / 8);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, cudaStream_t st) {
+  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < 64 && ld_dst % 8 == 0, "unpad_heads: head_dim must be a multiple of 8 below 64");
+  const long n = (long)T * H * (hd / 8);
+  if (n == 0) return 0;
+  unpad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, ld_dst / 8, n, H, hd / 8);
+  count_launch();
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // (log-)softmax over a short last dim (V <= 128): one warp per row
 // ---------------------------------------------------------------------------
 __global__ void softmax_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
