@@ -309,57 +309,67 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
                     const __nv_bfloat16* __restrict__ lnq, const __nv_bfloat16* __restrict__ lnk,
                     const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
                     const int32_t* __restrict__ pos) {
-  int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  // adjacent warps take the q and the k part of the same token: with q | k | v in one row the two parts are
+  // contiguous in memory, which keeps the DRAM pages of the row open for both
+  const int item = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int row = item >> 1, which = item & 1;
   int lane = threadIdx.x & 31;
   if (row >= T) return;
-  __nv_bfloat16* base = (blockIdx.y == 0 ? q : k) + (size_t)row * ld;
-  const __nv_bfloat16* lnw = blockIdx.y == 0 ? lnq : lnk;
+  __nv_bfloat16* base = (which == 0 ? q : k) + (size_t)row * ld;
+  const __nv_bfloat16* lnw = which == 0 ? lnq : lnk;
   uint4* xr = reinterpret_cast<uint4*>(base);
   const int D8 = D >> 3;
-  float v[NCH][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    int idx = c * 32 + lane;
-    if (idx < D8) {
-      unpack8(xr[idx], v[c]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[c][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
-    }
-  }
-  // From here on the row lives as packed bf16x2 words (4 per 8-element group): the roundings of the reference's
-  // bf16 elementwise ops are done by the packed conversions / HMUL2.BF16 / HADD2.BF16 instructions instead of
-  // scalar F2F conversions, which issue on the 16-lane XU pipe and made this kernel compute-bound.
+  // From here on the row lives as packed words: the LayerNorm statistics run on fp32 pairs (FADD2 / FFMA2 / FMUL2,
+  // same roundings, half the issue slots), the rotation on bf16x2 words whose roundings are produced by the packed
+  // conversions / HMUL2.BF16 / HADD2.BF16 instructions instead of scalar F2F conversions (16-lane XU pipe).
   uint4 pk[NCH];
   if (lnw != nullptr) {  // ESMC: q = bf(LN_w(q)) over the full embedding dim
-    const float mean = warp_sum(sum) / (float)D;
-    float sq = 0.f;
+    uint64_t v[NCH][4];
+    uint64_t acc = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      int idx = c * 32 + lane;
+      if (idx < D8) {
+        unpack8_f2(xr[idx], v[c]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = f2_add(acc, v[c][j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c][j] = f2_pack(0.f, 0.f);
+      }
+    }
+    float s0, s1;
+    f2_unpack(acc, s0, s1);
+    const float mean = warp_sum(s0 + s1) / (float)D;
+    const uint64_t nmean = f2_pack(-mean, -mean);
+    uint64_t sq = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
       if (c * 32 + lane < D8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { float d = v[c][j] - mean; sq += d * d; }
+        for (int j = 0; j < 4; ++j) {
+          v[c][j] = f2_add(v[c][j], nmean);
+          sq = f2_fma(v[c][j], v[c][j], sq);
+        }
       }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)D + 1e-5f);
+    f2_unpack(sq, s0, s1);
+    const float rstd = rsqrtf(warp_sum(s0 + s1) / (float)D + 1e-5f);
+    const uint64_t rstd2 = f2_pack(rstd, rstd);
     const uint4* w4 = reinterpret_cast<const uint4*>(lnw);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       int idx = c * 32 + lane;
-      float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      pk[c] = make_uint4(0, 0, 0, 0);
       if (idx < D8) {
-        float wf[8];
-        unpack8(__ldg(w4 + idx), wf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * wf[j];
+        uint64_t wf[4];
+        unpack8_f2(__ldg(w4 + idx), wf);
+        pk[c] = make_uint4(pack_bf16_f2(f2_mul(f2_mul(v[c][0], rstd2), wf[0])), pack_bf16_f2(f2_mul(f2_mul(v[c][1], rstd2), wf[1])),
+                           pack_bf16_f2(f2_mul(f2_mul(v[c][2], rstd2), wf[2])), pack_bf16_f2(f2_mul(f2_mul(v[c][3], rstd2), wf[3])));
       }
-      pk[c] = pack8(o);
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) pk[c] = pack8(v[c]);   // exact: the values are bf16 already
+    for (int c = 0; c < NCH; ++c) pk[c] = (c * 32 + lane < D8) ? xr[c * 32 + lane] : make_uint4(0, 0, 0, 0);
   }
   if (cosb != nullptr) {
     const int p = pos[row];
@@ -429,7 +439,7 @@ rope_pairs_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, 
 template <int NCH>
 static void launch_qk(void* q, void* k, int ld, int T, int D, int hd, const void* lnq, const void* lnk,
                       const void* cosb, const void* sinb, const int32_t* pos, cudaStream_t st) {
-  dim3 grid((T + kRowWarps - 1) / kRowWarps, 2);
+  dim3 grid((2 * T + kRowWarps - 1) / kRowWarps);
   qk_norm_rope_kernel<NCH><<<grid, kRowWarps * 32, 0, st>>>(
       (__nv_bfloat16*)q, (__nv_bfloat16*)k, ld, T, D, hd, (const __nv_bfloat16*)lnq, (const __nv_bfloat16*)lnk,
       (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, pos);
