@@ -67,3 +67,46 @@ def test_weight_packing_layouts():
     assert inter.shape == (2 * 512, D)
     assert torch.equal(inter[0:32], glu.activation.weight[0:32]) and torch.equal(inter[32:64], glu.fc.weight[0:32])
     assert torch.equal(inter[64:96], glu.activation.weight[32:64])
+
+
+def test_lora_host_plumbing(tmp_path):
+    """Module layout / state-dict keys / save-load of the LoRA drop-in, no kernels involved (reference
+    tests/test_lora.py:39-185)."""
+    from safetensors import safe_open
+    model = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors')
+    model.add_lora(16, 0.5, adapter_names=['x', 'y'], layers=['query', 'output'])
+    keys = set(model.lora_state_dict())
+    assert keys == {f'layers.{i}.self_attn.{j}.lora_{a}.{n}' for i in range(model.num_layers) for j in ('q', 'out')
+                    for a in 'AB' for n in 'xy'}
+    assert set(model.lora_state_dict(['x'])) == {k for k in keys if k.endswith('.x')}
+    assert 'layers.0.self_attn.q.layer.weight' in model.state_dict()          # the wrapped linear keeps its weights
+    model.mark_only_lora_as_trainable(['x'])
+    for n, p in model.named_parameters():
+        assert p.requires_grad == (('.lora_A.' in n or '.lora_B.' in n) and n.endswith('.x')), n
+    assert len(model.trainable_parameters()) == 2 * 2 * model.num_layers
+    path = str(tmp_path / 'lora.safetensors')
+    with torch.no_grad():
+        model.layers[0].self_attn.q.lora_B['x'].fill_(0.25)
+    model.save_lora(path)
+    with safe_open(path, 'pt') as f:
+        assert f.metadata()['rank'] == '16' and set(f.metadata()['names'].split(',')) == {'x', 'y'}
+    other = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors').load_lora(path)
+    assert torch.equal(other.layers[0].self_attn.q.lora_B['x'], model.layers[0].self_attn.q.lora_B['x'])
+    with pytest.raises(AssertionError):
+        model.add_lora(layers=['ffn'])
+
+
+def test_learned_positions_known_answers():
+    """esme/embedding.py docstring example and the packed variant (positions restart at padding_idx + 1 = 2)."""
+    from esme.embedding import LearnedPositionalEmbedding
+    emb = LearnedPositionalEmbedding(33, 8)
+    assert emb.weight.shape == (35, 8)
+    x = torch.tensor([[20, 29, 28], [8, 13, 9]])
+    assert emb.positions(x).tolist() == [[2, 3, 4], [2, 3, 4]]
+    assert emb.positions(torch.tensor([[0, 5, 2, 1, 1]])).tolist() == [[2, 3, 4, 1, 1]]    # padding stays at padding_idx
+    with pytest.raises(ValueError):
+        emb.positions(torch.zeros(1, 40, dtype=torch.long))
+    for cls in (esme.ESM1b, esme.ESM1v):
+        m = cls(num_layers=1, embed_dim=64, attention_heads=1, max_seq_len=32)
+        assert hasattr(m, 'emb_layer_norm_before') == (cls is esme.ESM1b)
+        assert m.layers[0].self_attn.rot_emb is None and m.embed_positions.weight.shape == (34, 64)
