@@ -55,3 +55,33 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
                 src = open(os.path.join(d, f)).read()
                 assert 'oracle' not in src, f'{f} references the oracle'
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/esmk.h compiles as C11 (no C++-isms in the ABI), the ctypes mirrors have the C struct sizes, and a C
+    program that takes the address of every declared entry point links against the shared library."""
+    import shutil
+    import subprocess
+    from esme import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    syms = _header_symbols()
+    src = tmp_path / 'abi_check.c'
+    src.write_text(
+        '#include <stdio.h>\n#include "esmk.h"\n'
+        'int main(void) {\n'
+        '  void (*fns[])(void) = {' + ', '.join(f'(void (*)(void))&{s}' for s in syms) + '};\n'
+        '  printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(fns) / sizeof(fns[0]), sizeof(esmk_gemm_args), sizeof(esmk_config),\n'
+        '         sizeof(esmk_layer_weights), sizeof(esmk_weights), sizeof(esmk_qweight));\n'
+        '  return esmk_version() >= 100 ? 0 : 1;\n}\n')
+    exe = tmp_path / 'abi_check'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(['gcc', '-std=c11', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(src),
+                        '-o', str(exe), '-L', libdir, '-lesmk', f'-Wl,-rpath,{libdir}'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    n, gemm, cfg, layer, weights, qw = map(int, out.stdout.split())
+    assert n == len(syms)
+    assert (gemm, cfg, layer, weights, qw) == (C.sizeof(_lib.GemmArgs), C.sizeof(_lib.Config), C.sizeof(_lib.LayerWeights),
+                                               C.sizeof(_lib.Weights), C.sizeof(_lib.QWeight))
