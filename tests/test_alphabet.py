@@ -83,3 +83,22 @@ def test_fast_tokenizer_path_is_identical_to_the_regex_path():
             if random.random() < 0.2:
                 s += '<mask>K'
             assert A._encode_rows([s], alpha)[0].tolist() == A._encode(A._TOKEN.findall(s), alpha), s
+
+
+def test_masked_lm_losses():
+    """esme.loss (reference esme/loss.py, tests/test_loss.py): scalar, positive, equal to the mean of the picked
+    negative log-probabilities, padding targets ignored."""
+    import torch
+    from esme.alphabet import Alphabet3
+    from esme.loss import cross_entropy, nll_loss
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(12, 33, generator=g)
+    logp = torch.log_softmax(logits, -1)
+    tokens = torch.randint(4, 24, (12,), generator=g)
+    tokens[3] = Alphabet3.padding_idx
+    mask = torch.zeros(12, dtype=torch.bool)
+    mask[[1, 3, 5, 8]] = True
+    want = -(logp[1, tokens[1]] + logp[5, tokens[5]] + logp[8, tokens[8]]) / 3
+    assert torch.allclose(nll_loss(logp, tokens, mask), want) and nll_loss(logp, tokens, mask).shape == ()
+    assert torch.allclose(cross_entropy(logits, tokens, mask), want)
+    assert torch.allclose(nll_loss(logp.reshape(3, 4, 33), tokens.reshape(3, 4), mask.reshape(3, 4)), want)
