@@ -7,16 +7,23 @@ One "step" = one forward pass (tokens -> logits) over one packed batch of synthe
 protein sequences (BASELINE config 2: <= 50,000 tokens per GPU, lognormal lengths,
 seeded synthetic bf16 weights).  For N > 1 (launched by torch.distributed.run, one rank
 per GPU) the global batch of N x 50k tokens is split by whole sequences across the ranks
-(esme.parallel), every rank runs the forward on its share and the logits are all-gathered
-(the one collective of the path): weak scaling.
+(esme.parallel.ShardPlan), every rank runs the forward on its share and the logits are
+all-gathered and put back into packed order (the one collective of the path): weak scaling.
 
-Prints ONE JSON line on rank 0.  `value` is device-timed with the batch resident in HBM;
-`e2e` repeats the measurement through the public API with pinned HOST buffers (H2D of the
-tokens and D2H of the logits inside the timed region).  `--impl reference` times the
-reference's algorithm on the host cores (the oracle port; the reference itself has no CPU
-path and cannot travel to the GPU box) on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+  value      device-timed (CUDA events, profiling OFF) with the batch resident in HBM
+  e2e        the same through the public API with pinned HOST buffers (H2D of the tokens and D2H of the
+             logits inside the timed region)
+  kernels    per-kernel-family times from a SEPARATE profiled loop (event pair around every launch)
+  roofline   the dominant GEMM against the measured sustained cuBLAS peak
+  gpu_reference   (N = 1) the UNMODIFIED reference package + flash-attn (oracle/_ref, child process) timed on the
+             same GPU, same weights and batch, right after the timed region; its logits compared with ours
+  attention_vs_flash_attn   the attention kernel alone against flash_attn_varlen_func on the same q, k, v
+  cpu_baseline / `--impl reference`   the reference on the HOST cores on a bounded sample (the unmodified package
+             with the SDPA substitution when oracle/_ref is present, else the oracle port)
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -36,6 +43,16 @@ MODELS = {
 }
 METRIC = 'residues_per_sec_forward'
 UNIT = 'residues/s'
+
+
+def load_synthetic():
+    """esme/synthetic.py loaded by file path: pure torch, and the CPU reference arm must not import the product
+    package (importing `esme` maps libesmk.so)."""
+    spec = importlib.util.spec_from_file_location(
+        '_esmk_synthetic', os.path.join(ROOT, 'esm-efficient_b200', 'esme', 'synthetic.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def measured_peaks():
@@ -91,68 +108,78 @@ class ClockSampler:
         return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
 
 
-def build_workload(args, rank, world):
-    """Global batch = world x budget tokens; returns this rank's share (host tensors) + bookkeeping."""
-    import torch
-    from esme import parallel, synthetic
-    family, layers, D, H = MODELS[args.model]
+def global_batch(args, world, synthetic):
+    """Global batch = world x (<= budget tokens): host tensors.  --batch-draw same (default) repeats ONE draw per
+    GPU, so the per-GPU work is exactly fixed as N grows (weak scaling measures the system, not the draw);
+    'distinct' draws a different 50k-token batch per GPU (seed 2 + 10 r)."""
+    family = MODELS[args.model][0]
     dist_name = 'loguniform' if family == 'esmc' else 'lognormal'
+    seed0 = 4 if family == 'esmc' else (5 if args.model == 'esm2_3b' else 2)     # SURVEY.md 8d seeds
+    if args.batch_draw == 'global':
+        lens = synthetic.synthetic_lengths(args.tokens * world, seed=seed0, dist=dist_name)
+        tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=3)
+        return lens, tokens, cu, max_len
     lens = []
-    for r in range(world):                       # one 50k-token draw per GPU -> weak scaling
-        lens += synthetic.synthetic_lengths(args.tokens, seed=2 + 10 * r, dist=dist_name)
+    for r in range(world):
+        lens += synthetic.synthetic_lengths(args.tokens, seed=seed0 + (10 * r if args.batch_draw == 'distinct' else 0),
+                                            dist=dist_name)
     tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=3)
-    if world > 1:
-        owned = parallel.partition_sequences(lens, world, D)
-        shares = [parallel.take_sequences(tokens, cu, o) for o in owned]
-        imb = parallel.imbalance(lens, owned, D)
-    else:
-        owned = [list(range(len(lens)))]
-        shares = [(tokens, cu, max_len, torch.arange(tokens.numel()))]
-        imb = 1.0
-    return dict(lens=lens, tokens=tokens, cu=cu, max_len=max_len, shares=shares, owned=owned, imbalance=imb)
+    return lens, tokens, cu, max_len
 
 
-def bounded_cpu_sample(wl, sample_tokens):
-    import torch
-    cu = wl['cu'].tolist()
-    n = 1
-    while n < len(cu) - 1 and cu[n + 1] <= sample_tokens:
-        n += 1
-    T = cu[n]
-    lens = [cu[i + 1] - cu[i] for i in range(n)]
-    return wl['tokens'][:T], wl['cu'][:n + 1].clone(), max(lens), T, n
-
-
-def run_cpu_reference(args, wl, W, steps, warmup, target_seconds=4.0):
-    """The reference algorithm on the host cores: oracle port, bf16-faithful mode, all threads."""
+def run_cpu_reference(args, lens, steps, warmup, target_seconds=4.0):
+    """The reference on the host cores, bounded sample of the same batch.  With oracle/_ref: the UNMODIFIED
+    reference package in a child process (flash_attn_varlen_func -> per-sequence SDPA, the reference has no CPU
+    attention) -- kind 'reference'.  Without: the oracle port (bf16-faithful mode) -- kind 'port'."""
+    family, layers, D, H = MODELS[args.model]
+    from oracle import ref_client as RC
+    if RC.ref_available():
+        info, _ = RC.run_reference(dict(
+            device='cpu', family=family, num_layers=layers, embed_dim=D, attention_heads=H,
+            weights={'synthetic_seed': 1}, mode='time', steps=steps, warmup=warmup,
+            method='predict_log_prob' if family == 'esmc' else 'forward',
+            sample={'target_seconds': target_seconds, 'min_tokens': 512, 'max_tokens': 8192},
+            batch={'lens': lens, 'seed': 3}), timeout=1500)
+        sec = info['ms_per_step'] / 1e3
+        return dict(value=info['tokens'] / sec, unit=UNIT, cores=info['threads'], kind='reference',
+                    sample=f'{info["sample"]}, {steps} timed forward(s) after {warmup} warm-up, unmodified reference '
+                           f'package (oracle/_ref) in bf16 on torch-cpu, {info["threads"]} threads of {info["cores"]} '
+                           f'host cores, {info["attention"]} in place of flash-attn'), sec
     import torch
     from oracle import esm_oracle as O
-    family, layers, D, H = MODELS[args.model]
+    synthetic = load_synthetic()
+    W = synthetic.synthetic_state_dict(family, layers, D, seed=1)
+    tokens, cu, _ = synthetic.synthetic_batch(lens, seed=3)
     cfg = O.OracleConfig(family, layers, D, H)
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    # pilot on ~256 tokens to size the bounded sample (~target_seconds of CPU work per step)
-    tok, cu, ml, T0, _ = bounded_cpu_sample(wl, 256)
+
+    def prefix(limit):
+        c = cu.tolist()
+        n = 1
+        while n < len(c) - 1 and c[n + 1] <= limit:
+            n += 1
+        return tokens[:c[n]], cu[:n + 1].clone(), max(c[i + 1] - c[i] for i in range(n)), c[n], n
+    tok, c, ml, T0, _ = prefix(256)
     t0 = time.perf_counter()
-    O.forward_packed(cfg, W, tok, cu, ml, 'bf16')
-    pilot = time.perf_counter() - t0
-    rate = T0 / pilot
-    sample_tokens = int(min(max(rate * target_seconds, 512), 8192))
-    tok, cu, ml, T, nseq = bounded_cpu_sample(wl, sample_tokens)
+    O.forward_packed(cfg, W, tok, c, ml, 'bf16')
+    rate = T0 / (time.perf_counter() - t0)
+    tok, c, ml, T, nseq = prefix(int(min(max(rate * target_seconds, 512), 8192)))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_packed(cfg, W, tok, cu, ml, 'bf16')
+        O.forward_packed(cfg, W, tok, c, ml, 'bf16')
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return dict(value=T / sec, unit=UNIT, cores=cores, kind='port',
-                sample=f'first {nseq} sequences ({T} tokens) of the same batch, {steps} timed forward(s), '
-                       f'oracle/esm_oracle.py bf16-faithful mode, torch CPU fp32 GEMMs on {cores} threads'), sec
+                sample=f'first {nseq} sequences ({T} tokens) of the batch, {steps} timed forward(s), '
+                       f'oracle/esm_oracle.py bf16-faithful mode, torch CPU fp32 GEMMs on {cores} threads '
+                       f'(oracle/_ref absent)'), sec
 
 
 def bench_mask_margin(args, family, layers, D, H):
-    """BASELINE config 5 (bf16 part): masked-marginal sweep of one 1,024-residue protein, batch 32 ->
+    """BASELINE config 5: masked-marginal sweep of one 1,024-residue protein, batch 32 ->
     32 forwards of 32 x 1,026 tokens; residues/s = 1024 * 1026 / sweep time (single GPU)."""
     import torch
     import esme
@@ -167,28 +194,34 @@ def bench_mask_margin(args, family, layers, D, H):
     model = model.to(dev).eval().requires_grad_(False)
     g = torch.Generator().manual_seed(6)
     seq = ''.join(Alphabet.amino_acids[int(i)] for i in torch.randint(0, 20, (1024,), generator=g))
-    quant_note, score_check = 'bf16 weights', None
+    quant_note, score_check, bf16_sec = 'bf16 weights', None, None
+    sampler = ClockSampler(0)
+
+    def sweep_time(m):
+        for _ in range(max(1, args.warmup // 3)):
+            predict_mask_margin(m, seq, batch_size=32)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = predict_mask_margin(m, seq, batch_size=32)        # ends with the single D2H of the scores
+        return (time.perf_counter() - t0) / args.steps, out, _lib.launch_count() - n0
     if args.quant != 'none':
-        # BASELINE config 5: int4 weight-quantised FFN.  Scores of the bf16 model first, for the comparison.
+        # BASELINE config 5: int4 weight-quantised FFN.  Scores (and the sweep time) of the bf16 model first.
         from esme.quantization import quantize_model_
-        base = predict_mask_margin(model, seq, batch_size=32)
+        bf16_sec, base, _ = sweep_time(model)
         which = ('ffn',) if args.quant.endswith('ffn') else ('q', 'k', 'v', 'out', 'ffn')
         quantize_model_(model, 4 if args.quant.startswith('4bit') else 8, which=which)
-        quant_note = f'{args.quant} weight-only quantised linears (esme/quantization.py formats), GEMMs in bf16 on the dequantised weight'
-    for _ in range(max(1, args.warmup // 3)):
-        predict_mask_margin(model, seq, batch_size=32)
-    torch.cuda.synchronize()
-    launches0 = _lib.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        df = predict_mask_margin(model, seq, batch_size=32)        # ends with the single D2H of the scores
-    sec = (time.perf_counter() - t0) / args.steps
+        quant_note = f'{args.quant} weight-only quantised linears (esme/quantization.py formats)'
+    sec, df, launches = sweep_time(model)
+    clocks = sampler.stop()
     if args.quant != 'none':
         a = torch.tensor(base['score'].to_numpy(), dtype=torch.float64)
         b = torch.tensor(df['score'].to_numpy(), dtype=torch.float64)
         ra, rb = a.argsort().argsort().double(), b.argsort().argsort().double()
         score_check = {'spearman_vs_bf16': float(torch.corrcoef(torch.stack((ra, rb)))[0, 1]),
-                       'mean_abs_diff_vs_bf16': float((a - b).abs().mean()), 'max_abs_diff_vs_bf16': float((a - b).abs().max())}
+                       'mean_abs_diff_vs_bf16': float((a - b).abs().mean()), 'max_abs_diff_vs_bf16': float((a - b).abs().max()),
+                       'bf16_sweep_ms': bf16_sec * 1e3, 'quantised_over_bf16_time': sec / bf16_sec}
     print(json.dumps({
         'metric': 'residues_per_sec_mask_margin_sweep', 'value': 1024 * 1026 / sec, 'unit': UNIT, 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
@@ -197,7 +230,101 @@ def bench_mask_margin(args, family, layers, D, H):
                                f'32 packed forwards of 32 x 1,026 tokens, LM head on the 1,024 masked rows only, '
                                f'one D2H of the [1024, 20] score matrix; wall-clock incl. host-side DataFrame',
                    'rows': int(df.shape[0]), 'weights': quant_note, 'scores_vs_bf16': score_check},
-        'gpu_launches': _lib.launch_count() - launches0}))
+        'clocks': clocks, 'gpu_launches': launches}))
+
+
+def err_stats(a, b):
+    import torch
+    a = a.double().reshape(-1, a.shape[-1])
+    b = b.double().reshape(-1, b.shape[-1])
+    return dict(max_abs=(a - b).abs().max().item(),
+                rms_rel=((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item(),
+                min_row_cosine=torch.nn.functional.cosine_similarity(a, b, dim=-1).min().item(),
+                argmax_agreement=(a.argmax(-1) == b.argmax(-1)).double().mean().item())
+
+
+def gpu_reference_block(args, lens, ms_step, logits_new, model_args):
+    """The reference's flash-attn GPU build timed beside the product: same GPU, same weights, same batch."""
+    import torch
+    family, layers, D, H = model_args
+    from oracle import ref_client as RC
+    T = sum(lens)
+    try:
+        if RC.ref_available():
+            info, outs = RC.run_reference(dict(
+                device='cuda', family=family, num_layers=layers, embed_dim=D, attention_heads=H,
+                weights={'synthetic_seed': 1}, mode='time', steps=max(3, min(args.steps, 10)), warmup=3,
+                method='predict_log_prob' if family == 'esmc' else 'forward',
+                batch={'lens': lens, 'seed': 3}), timeout=900)
+            ms, kind, y_ref = info['ms_per_step'], 'real', outs.get('out')
+            what = (f'unmodified reference package (oracle/_ref/esme) + {info["attention"]}, child process on the same '
+                    f'GPU, {info["steps"]} timed forwards after {info["warmup"]} warm-up, CUDA events')
+        elif family == 'esm2':
+            from oracle.restated_gpu import reference_gpu_forward
+            synthetic = load_synthetic()
+            dev = logits_new.device
+            W = {k: v.to(dev) for k, v in synthetic.synthetic_state_dict(family, layers, D, seed=1).items()}
+            tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=3)
+            tokens, cu = tokens.to(dev), cu.to(dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    y = reference_gpu_forward(W, layers, D, H, tokens, cu, max_len)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    y = reference_gpu_forward(W, layers, D, H, tokens, cu, max_len)
+                e1.record()
+                torch.cuda.synchronize()
+            ms, kind, y_ref = e0.elapsed_time(e1) / 3, 'restated', y.float().cpu()
+            what = 'reference op sequence restated on torch/cuBLAS/flash-attn (oracle/restated_gpu.py); oracle/_ref absent'
+        else:
+            return {'unavailable': 'oracle/_ref absent and no restatement for this family'}
+    except Exception as e:  # the comparator must never take the bench line down
+        return {'unavailable': f'{type(e).__name__}: {str(e)[-300:]}'}
+    block = dict(kind=kind, ms_per_step=ms, value=T / ms * 1e3, unit=UNIT, speedup=ms / ms_step, what=what)
+    if y_ref is not None:
+        block['new_vs_reference_logits'] = err_stats(logits_new.float().cpu(), y_ref)
+    return block
+
+
+def attention_vs_flash_block(D, H, lens, dev):
+    """The attention kernel alone against flash_attn_varlen_func (the op it replaces, esme/attention.py:115-123)
+    on the same random bf16 q, k, v of the bench batch's shape."""
+    import torch
+    try:
+        from flash_attn import flash_attn_varlen_func
+        from esme import ops
+        hd = D // H
+        T = sum(lens)
+        g = torch.Generator(device=dev).manual_seed(5)
+        qkv = torch.randn(T, 3 * D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        q, k, v = (qkv[:, i * D:(i + 1) * D].view(T, H, hd) for i in range(3))
+        cu = torch.zeros(len(lens) + 1, dtype=torch.int32, device=dev)
+        cu[1:] = torch.cumsum(torch.tensor(lens, dtype=torch.int32, device=dev), 0)
+        max_len = max(lens)
+        _, tile_info = ops.batch_meta(cu, T)
+
+        def timeit(fn, n=20):
+            for _ in range(3):
+                y = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                y = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n, y
+        ms_fa, y_fa = timeit(lambda: flash_attn_varlen_func(q, k, v, cu, cu, max_len, max_len, dropout_p=0.0, causal=False))
+        ms_new, y_new = timeit(lambda: ops.attn_varlen(q, k, v, cu, max_len, tile_info))
+        flops = 4.0 * D * sum(l * l for l in lens)
+        return dict(flash_attn_ms=ms_fa, esmk_ms=ms_new, speedup=ms_fa / ms_new, esmk_tflops=flops / ms_new / 1e9,
+                    flash_attn_tflops=flops / ms_fa / 1e9,
+                    max_abs_diff=(y_new.float() - y_fa.reshape(T, D).float()).abs().max().item(),
+                    what='20 back-to-back launches each on the same q, k, v (L2-warm), CUDA events')
+    except Exception as e:
+        return {'unavailable': f'{type(e).__name__}: {str(e)[-300:]}'}
 
 
 def main():
@@ -208,7 +335,11 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--model', default='esm2_650m', choices=sorted(MODELS))
     ap.add_argument('--tokens', type=int, default=50000, help='token budget per GPU')
+    ap.add_argument('--batch-draw', default='same', choices=['same', 'distinct', 'global'],
+                    help='N > 1: every GPU gets a copy of the same <=tokens draw (default), its own draw, or one '
+                         'draw of N x tokens is partitioned (BASELINE config 4: --model esm2_3b --tokens 25000 --batch-draw global)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-reference', action='store_true')
     ap.add_argument('--quant', default='none', choices=['none', '4bit-ffn', '4bit', '8bit-ffn', '8bit'],
                     help='weight-only quantisation of the layer linears (mask_margin workload; BASELINE config 5 = 4bit-ffn)')
     ap.add_argument('--workload', default='forward', choices=['forward', 'mask_margin'],
@@ -221,16 +352,14 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     family, layers, D, H = MODELS[args.model]
 
-    import torch
-    from esme import synthetic
-
     if args.impl == 'reference':
         if rank != 0:
             return
-        wl = build_workload(args, 0, 1)
-        W = synthetic.synthetic_state_dict(family, layers, D, seed=1)
+        synthetic = load_synthetic()
+        lens, _, _, _ = global_batch(args, 1, synthetic)
         steps = max(1, min(args.steps, 5))
-        base, sec = run_cpu_reference(args, wl, W, steps, 1)
+        base, sec = run_cpu_reference(args, lens, steps, 1)
+        assert not any('libesmk' in l for l in open('/proc/self/maps')), 'the CPU reference arm must not map libesmk.so'
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': steps, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
@@ -246,48 +375,47 @@ def main():
         return bench_mask_margin(args, family, layers, D, H)
 
     # ------------------------------------------------------------------ B200 arm
+    import torch
     import torch.distributed as dist
     import esme
-    from esme import _lib, parallel
+    from esme import _lib, parallel, synthetic
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device (no CPU fallback exists)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    wl = build_workload(args, rank, world)
+    lens, tokens_g, cu_g, max_len_g = global_batch(args, world, synthetic)
+    plan = parallel.ShardPlan(tokens_g, cu_g, world, rank, D, dev)
     W = synthetic.synthetic_state_dict(family, layers, D, seed=1)
     cls = esme.ESMC if family == 'esmc' else esme.ESM2
     model = cls(layers, D, H)
     model.load_state_dict(W, strict=True)
     model = model.to(dev).eval().requires_grad_(False)
+    del W
     V = model.lm_head.final.out_features
 
-    tok_h, cu_h, max_len, token_index = wl['shares'][rank]
-    T_local, T_global = tok_h.numel(), wl['tokens'].numel()
+    tok_h, cu_h, max_len = plan.tokens, plan.cu_lens, plan.max_len
+    T_local, T_global = tok_h.numel(), tokens_g.numel()
     tok_pin, cu_pin = tok_h.pin_memory(), cu_h.pin_memory()
     tok_d, cu_d = tok_pin.to(dev), cu_pin.to(dev)
-    t_max = max(s[0].numel() for s in wl['shares'])
-    gather_buf = torch.empty(world * t_max, V, dtype=torch.bfloat16, device=dev) if world > 1 else None
-    local_buf = torch.zeros(t_max, V, dtype=torch.bfloat16, device=dev) if world > 1 else None
-    out_pin = torch.empty((world * t_max if world > 1 else T_local, V), dtype=torch.bfloat16).pin_memory()
+    # e2e result buffers: rank 0 holds the whole gathered batch on the host, the others their own slice
+    out_pin = torch.empty((T_global if rank == 0 else T_local, V), dtype=torch.bfloat16).pin_memory()
 
     # BASELINE config 3 (ESMC) is quoted on predict_log_prob; the ESM2 configs on forward (logits)
     forward = model.predict_log_prob if family == 'esmc' else model.__call__
 
     def step(tokens, cu):
         logits = forward(tokens, (cu, max_len))
-        if world > 1:                       # the single collective of the path: all-gather of logits
-            local_buf[:T_local] = logits
-            dist.all_gather_into_tensor(gather_buf, local_buf)
-            return gather_buf
-        return logits
+        if world > 1:                       # the single collective of the path + restoring the packed order
+            return logits, plan.gather(logits)
+        return logits, logits
 
     def e2e_step():
         t = tok_pin.to(dev, non_blocking=True)
         c = cu_pin.to(dev, non_blocking=True)
-        out = step(t, c)
-        out_pin.copy_(out, non_blocking=True)
+        local, full = step(t, c)
+        out_pin.copy_(full if rank == 0 else local, non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the caller holds the logits on the host
 
     def sync_all():
@@ -296,7 +424,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, reduce_max=True):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -305,7 +433,7 @@ def main():
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
-        if world > 1:
+        if world > 1 and reduce_max:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
@@ -313,40 +441,74 @@ def main():
         step(tok_d, cu_d)
     sync_all()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- the timed region: K steps, profiling OFF, clocks sampled meanwhile
+    sampler = ClockSampler(local_rank)
     launches0 = _lib.launch_count()
-    _lib.profile_enable(True)                      # CUDA-event pairs around every launch of the timed steps
     ms_step = timed(lambda: step(tok_d, cu_d), args.steps)
-    prof = _lib.profile_read()
-    _lib.profile_enable(False)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
 
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- separate loops: per-rank forward / collective split, per-kernel-family profile
+    ms_fwd_local = timed(lambda: forward(tok_d, (cu_d, max_len)), max(3, args.steps // 2), reduce_max=False)
+    ms_gather_local = 0.0
+    local_logits, full_logits = step(tok_d, cu_d)
+    if world > 1:
+        ms_gather_local = timed(lambda: plan.gather(local_logits), 10, reduce_max=False)
+    _lib.profile_enable(True)                      # CUDA-event pairs around every launch
+    prof_steps = 3
+    timed(lambda: forward(tok_d, (cu_d, max_len)), prof_steps, reduce_max=False)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+
+    local_lens = [int(x) for x in (cu_h[1:] - cu_h[:-1]).tolist()]
+    fl = synthetic.forward_flops(family, layers, D, local_lens)
+    per_rank = None
+    sharded_ok = None
+    if world > 1:
+        mine = dict(rank=rank, tokens=T_local, sequences=len(local_lens), ms_forward=ms_fwd_local,
+                    ms_allgather_restore=ms_gather_local, algorithmic_tflop=fl['total'] / 1e12,
+                    model_tflops=fl['total'] / ms_fwd_local / 1e9, sm_mhz=clocks.get('sm_mhz'), reasons=clocks.get('reasons'))
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        if rank == 0:
+            # sharded == single: rank 0 runs the un-sharded forward on a <= 8k-token prefix of the GLOBAL batch and
+            # compares with the gathered, order-restored result (batch invariance makes this bit-exact)
+            c = cu_g.tolist()
+            n = 1
+            while n < len(c) - 1 and c[n + 1] <= 8192:
+                n += 1
+            sub_len = max(c[i + 1] - c[i] for i in range(n))
+            single = forward(tokens_g[:c[n]].to(dev), (cu_g[:n + 1].to(dev), sub_len))
+            sharded_ok = bool(torch.equal(single, full_logits[:c[n]]))
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (tensor bound), measured live over the timed steps
+    # ---- roofline of the dominant kernel (tensor bound), from the profiled loop
     peaks = measured_peaks()
-    fl = synthetic.forward_flops(family, layers, D, [int(x) for x in (cu_h[1:] - cu_h[:-1]).tolist()])
     F = synthetic.ffn_dim(family, D)
     per_launch_flops = {
         'gemm_qkv': 2.0 * T_local * D * 3 * D, 'gemm_out': 2.0 * T_local * D * D,
         'gemm_ffn_up': 2.0 * T_local * D * (F if family == 'esm2' else 2 * F), 'gemm_ffn_down': 2.0 * T_local * F * D,
         'attention': fl['attention'] / layers,
     }
+    per_launch_bytes = {'layernorm': 2.0 * T_local * D * 2}
     kernels = {}
     for name, (ms, n) in prof.items():
         if n == 0:
             continue
-        k = dict(ms_per_step=ms / args.steps, launches_per_step=n / args.steps, avg_launch_ms=ms / n)
+        k = dict(ms_per_step=ms / prof_steps, launches_per_step=n / prof_steps, avg_launch_ms=ms / n)
         if name in per_launch_flops:
             k['tflops'] = per_launch_flops[name] / (ms / n) / 1e9
+        if name in per_launch_bytes:
+            k['gbs'] = per_launch_bytes[name] / (ms / n) / 1e6
+            k['frac_of_hbm_peak'] = k['gbs'] / peaks['hbm_gbs']
         kernels[name] = k
     gemm_names = [n for n in ('gemm_qkv', 'gemm_out', 'gemm_ffn_up', 'gemm_ffn_down') if n in kernels]
     dominant = max(gemm_names, key=lambda n: kernels[n]['ms_per_step'])
@@ -360,17 +522,26 @@ def main():
                     peak_source=peaks['source'] + ', bf16_tflops_sustained (kernel timed inside a long step)',
                     algorithmic_flops_per_launch=per_launch_flops[dominant],
                     avg_launch_ms=kernels[dominant]['avg_launch_ms'],
+                    timed_in='separate profiled loop (event pair around every launch), not the `value` loop',
                     all_gemms_tflops=sum(per_launch_flops[n] * kernels[n]['launches_per_step'] for n in gemm_names)
                     / sum(kernels[n]['ms_per_step'] for n in gemm_names) / 1e9,
                     attention_tflops=kernels.get('attention', {}).get('tflops'),
                     attention_frac_of_burst_peak=(kernels['attention']['tflops'] / peaks['bf16_tflops']
-                                                  if 'attention' in kernels else None))
+                                                  if 'attention' in kernels else None),
+                    attention_frac_of_sustained_peak=(kernels['attention']['tflops'] / peak
+                                                      if 'attention' in kernels else None))
 
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = run_cpu_reference(args, wl, W, steps=1, warmup=0, target_seconds=12.0)
+    gpu_ref = attn_cmp = cpu_base = None
+    if world == 1:
+        hd = D // H
+        if hd == 64:
+            attn_cmp = attention_vs_flash_block(D, H, local_lens, dev)
+        if not args.no_gpu_reference:
+            gpu_ref = gpu_reference_block(args, lens, ms_step, local_logits, (family, layers, D, H))
+        if not args.no_cpu_baseline:
+            cpu_base, _ = run_cpu_reference(args, lens, steps=1, warmup=0, target_seconds=12.0)
 
-    residues = sum(l - 2 for l in wl['lens'])
+    residues = sum(l - 2 for l in lens)
     result = {
         'metric': METRIC, 'value': T_global / ms_step * 1e3, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -379,12 +550,13 @@ def main():
             'workload': f'{args.model} {"predict_log_prob" if family == "esmc" else "forward (tokens -> logits)"}, packed batch <= {args.tokens} tokens per GPU, '
                         f'{"log-uniform 128-2048" if family == "esmc" else "lognormal(400, 0.75) clipped 30-3500"} '
                         f'residue lengths, seeded synthetic bf16 weights',
-            'tokens_global': T_global, 'tokens_this_rank': T_local, 'sequences_global': len(wl['lens']),
-            'max_len': wl['max_len'], 'residues_excl_cls_eos': residues,
+            'tokens_global': T_global, 'tokens_this_rank': T_local, 'sequences_global': len(lens),
+            'max_len': max_len_g, 'residues_excl_cls_eos': residues,
             'residues_are': 'packed tokens incl. <cls>/<eos> (SURVEY.md 8d)',
             'parallelism': f'dp{world}: whole sequences per rank (LPT on a*L + b*L^2), replicated weights'
-                           + (', NCCL all-gather of logits inside the step' if world > 1 else ''),
-            'partition_imbalance_max_over_mean': wl['imbalance'],
+                           + (', NCCL all-gather of logits + packed-order restore inside the step' if world > 1 else ''),
+            'batch_draw': args.batch_draw + (' (every GPU gets a copy of one draw: per-GPU work fixed)' if args.batch_draw == 'same' else ''),
+            'partition_imbalance_max_over_mean': plan.imbalance,
             'l2_policy': 'inputs larger than L2: every step streams 1.3 GB of weights and ~1.3 GB of activations '
                          'per layer through a 126 MB L2; no explicit flush',
             'algorithmic_tflop_per_step_this_rank': fl['total'] / 1e12,
@@ -397,10 +569,18 @@ def main():
         'roofline': roofline,
         'kernels': kernels,
         'model_tflops': fl['total'] / ms_step / 1e9,
+        'ms_forward_this_rank': ms_fwd_local,
+        'gpu_reference': gpu_ref,
+        'attention_vs_flash_attn': attn_cmp,
         'cpu_baseline': cpu_base,
     }
+    if world > 1:
+        result['sharded_matches_single'] = sharded_ok
+        result['per_rank'] = per_rank
+        result['ms_allgather_restore'] = max(p['ms_allgather_restore'] for p in per_rank)
     print(json.dumps(result))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

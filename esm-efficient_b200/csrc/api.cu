@@ -16,6 +16,7 @@ uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define GUARD(expr)                                   \
   try {                                               \
+    if (int _async = ::esmk::consume_async_error()) return _async; \
     return (expr);                                    \
   } catch (const std::exception& e) {                 \
     return ::esmk::fail("esmk", e.what());            \
@@ -28,6 +29,13 @@ extern "C" {
 const char* esmk_last_error(void) { return esmk::last_error().c_str(); }
 int esmk_version(void) { return 100; }
 uint64_t esmk_launch_count(void) { return esmk::launch_count(); }
+int esmk_async_error(void) {
+  uint32_t* w = esmk::async_error_word();
+  if (w == nullptr) return 0;
+  const uint32_t code = *reinterpret_cast<volatile uint32_t*>(w);
+  *reinterpret_cast<volatile uint32_t*>(w) = 0;
+  return (int)code;
+}
 
 int esmk_tile_capacity(int T, int B) { return (T < 0 || B < 0) ? 0 : esmk::tile_capacity(T, B); }
 int esmk_batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile_info, esmk_stream_t s) {

@@ -677,13 +677,15 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     // share of the exponentials evaluated on the FMA pipes (eighths); ESMK_ATTN_POLY=1 selects the 3/8 variant (A/B measurements)
     using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
                               long long*, long long*);
-    static kernel_t kernel = nullptr;
-    if (kernel == nullptr) {
+    static const kernel_t kernel = [] {
       int poly = kDefaultPoly;
       if (const char* e = getenv("ESMK_ATTN_POLY")) poly = atoi(e);
-      kernel_t k = poly <= 0 ? attn64_kernel<0> : attn64_kernel<3>;   // 3/8 of the exponentials on the FMA pipes
-      ESMK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      kernel = k;
+      return poly <= 0 ? attn64_kernel<0> : attn64_kernel<3>;         // 3/8 of the exponentials on the FMA pipes
+    }();
+    static std::atomic<uint64_t> configured{0};                       // per device: a process may use several GPUs
+    if (needs_config(configured)) {
+      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      mark_configured(configured);
     }
     // heads per CTA: amortise the per-CTA start-up over up to 4 heads while keeping >= ~8 CTAs per SM slot
     int hpc = 1;

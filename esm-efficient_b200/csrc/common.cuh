@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace esmk {
@@ -38,7 +39,16 @@ int check_cuda(cudaError_t e, const char* where);
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
-int sm_count();
+// device-detected data errors (see util.cu): sticky word in mapped pinned memory, checked at every API entry
+uint32_t* async_error_word();      // host == device address (UVA); nullptr if the allocation failed
+int consume_async_error();         // 0, or fail(...) with the decoded message (and the word cleared)
+
+constexpr int kMaxDevices = 64;
+int current_device();
+int sm_count();   // of the current device
+// per-device one-time kernel configuration (cudaFuncSetAttribute is per device / context)
+bool needs_config(std::atomic<uint64_t>& mask);
+void mark_configured(std::atomic<uint64_t>& mask);
 // Programmatic dependent launch (ESMK_PDL=0 disables): kernels launched with this attribute may be scheduled while
 // the previous kernel on the stream is still draining; they call griddep_wait() before touching global memory.
 bool pdl_enabled();

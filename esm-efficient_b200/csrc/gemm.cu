@@ -1,9 +1,12 @@
 // C[M,N] = epilogue(A[M,K] . W[N,K]^T): persistent, warp-specialised tcgen05 GEMM.
 //
-//   warp 0      : TMA producer (A 128x64 and W 256x64 bf16 tiles, SWIZZLE_128B, 4-stage ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, fp32 accum in TMEM)
-//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused math -> 16-byte global stores);
-//                 two warps per TMEM lane quadrant, each owning one 128-column half of the tile
+// Default (PAIR) mode: a cluster of two CTAs computes one 256x256 tile with cta_group::2 UMMA 256x256x16.
+//   warp 0      : TMA producer (own 128 rows of A + half of the W tile per stage, SWIZZLE_128B, 6-stage ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (leader CTA; fp32 accumulators in TMEM)
+//   warps 2..17 : epilogue for bias / GELU / residual (tcgen05.ld 32x32b -> registers -> fused math -> swizzled
+//                 shared-memory staging -> TMA store); four warps per TMEM lane quadrant, 64 columns each.
+//                 QKV+RoPE and SwiGLU keep 8 epilogue warps (two per quadrant, 128 columns each).
+// (ESMK_GEMM_PAIR=0: one CTA per 128x256 tile, UMMA 128x256x16, 4-stage ring.)
 //
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.  Tiles are walked n-fastest so the CTAs
@@ -769,10 +772,10 @@ template <int EPI, int HD, bool PAIR>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
                 const EpiParams& ep, cudaStream_t st) {
   auto kern = gemm_kernel<EPI, HD, PAIR>;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};   // per device: a process may use several GPUs
+  if (needs_config(configured)) {
     ESMK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+    mark_configured(configured);
   }
   const int tile_m = PAIR ? 2 * BM : BM;
   const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);

@@ -142,12 +142,14 @@ int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 __global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint4* __restrict__ table,
                              uint4* __restrict__ out, int T, int D8, int vocab, int zero_token,
-                             const uint8_t* __restrict__ zero_rows) {
+                             const uint8_t* __restrict__ zero_rows, uint32_t* __restrict__ err) {
   int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= T) return;
   long long tok = tokens[row];
-  bool zero = (tok == zero_token) || (zero_rows != nullptr && zero_rows[row] != 0) || tok < 0 || tok >= vocab;
+  const bool bad = tok < 0 || tok >= vocab;      // reported (sticky error word), the row is zero-filled meanwhile
+  if (bad && lane == 0 && err != nullptr) *reinterpret_cast<volatile uint32_t*>(err) = ESMK_ASYNC_BAD_TOKEN;
+  bool zero = (tok == zero_token) || (zero_rows != nullptr && zero_rows[row] != 0) || bad;
   const uint4* src = table + (size_t)(zero ? 0 : tok) * D8;
   uint4* dst = out + (size_t)row * D8;
   for (int c = lane; c < D8; c += 32) dst[c] = zero ? make_uint4(0, 0, 0, 0) : __ldg(src + c);
@@ -157,7 +159,7 @@ int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int
           const uint8_t* zero_rows, cudaStream_t st) {
   ESMK_REQUIRE(D % 8 == 0, "embed_dim must be a multiple of 8");
   embed_kernel<<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
-      tokens, (const uint4*)table, (uint4*)out, T, D / 8, vocab, zero_token, zero_rows);
+      tokens, (const uint4*)table, (uint4*)out, T, D / 8, vocab, zero_token, zero_rows, async_error_word());
   count_launch();
   ESMK_CUDA(cudaGetLastError());
   return 0;
@@ -166,10 +168,12 @@ int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int
 // ESM-1b / ESM-1v: x[t] = bf(x[t] + P[pos[t] + offset]) in place (esme/esm.py:634-646, esme/embedding.py:36-92:
 // learned positions count from padding_idx + 1 inside each sequence)
 __global__ void add_positions_kernel(uint4* __restrict__ x, const uint4* __restrict__ table, const int32_t* __restrict__ pos,
-                                     int T, int D8, int rows, int offset) {
+                                     int T, int D8, int rows, int offset, uint32_t* __restrict__ err) {
   int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= T) return;
+  if (pos[row] + offset >= rows && lane == 0 && err != nullptr)
+    *reinterpret_cast<volatile uint32_t*>(err) = ESMK_ASYNC_BAD_POSITION;
   const int p = min(max(pos[row] + offset, 0), rows - 1);
   const uint4* src = table + (size_t)p * D8;
   uint4* dst = x + (size_t)row * D8;
@@ -183,7 +187,7 @@ int add_positions(void* x, const void* table, const int32_t* pos, int T, int D, 
   ESMK_REQUIRE(x && table && pos && D % 8 == 0 && rows >= 1, "add_positions: bad arguments");
   if (T == 0) return 0;
   add_positions_kernel<<<(T + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>((uint4*)x, (const uint4*)table, pos, T, D / 8,
-                                                                                 rows, offset);
+                                                                                 rows, offset, async_error_word());
   count_launch();
   ESMK_CUDA(cudaGetLastError());
   return 0;

@@ -3,7 +3,9 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "esmk_internal.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace esmk {
@@ -22,6 +24,42 @@ int check_cuda(cudaError_t e, const char* where) {
   if (e == cudaSuccess) return 0;
   g_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
   return 2;
+}
+
+// ---------------------------------------------------------------------------
+// Asynchronous (device-detected) errors: one sticky word in mapped pinned host memory (same address on the host and on
+// every device under UVA).  Kernels that meet invalid DATA (a token id outside the embedding table, a position
+// beyond the learned positional table) OR a code into it -- a zero-copy store that only happens on the error path --
+// and every C-ABI entry point checks it before doing anything else: the failure surfaces at the next API call
+// after the offending kernel ran (the reference would hit a device-side assert at its next synchronisation).
+// ---------------------------------------------------------------------------
+uint32_t* async_error_word() {
+  static uint32_t* word = [] {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, sizeof(uint32_t), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      return static_cast<uint32_t*>(nullptr);
+    }
+    *static_cast<volatile uint32_t*>(p) = 0;
+    return static_cast<uint32_t*>(p);
+  }();
+  return word;
+}
+
+int consume_async_error() {
+  static uint32_t* word = nullptr;
+  if (word == nullptr) {
+    word = async_error_word();
+    if (word == nullptr) return 0;
+  }
+  const uint32_t code = *reinterpret_cast<volatile uint32_t*>(word);
+  if (code == 0) return 0;
+  *reinterpret_cast<volatile uint32_t*>(word) = 0;
+  std::string msg = "a previous kernel reported invalid input data:";
+  if (code & ESMK_ASYNC_BAD_TOKEN) msg += " token id outside [0, embedding rows) in esmk_embed / esmk_forward;";
+  if (code & ESMK_ASYNC_BAD_POSITION) msg += " sequence longer than the learned positional table in esmk_add_positions;";
+  msg += " the outputs of that call are invalid";
+  return fail("esmk (asynchronous)", msg);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -70,14 +108,34 @@ bool pdl_enabled() {
   return on;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  if (dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// cudaFuncSetAttribute is per device (context): `mask` remembers on which devices a kernel was configured
+bool needs_config(std::atomic<uint64_t>& mask) {
+  const int dev = current_device();
+  if (dev >= kMaxDevices) return true;                       // beyond the bitmask: configure every time
+  return (mask.load(std::memory_order_acquire) & (1ull << dev)) == 0;
+}
+void mark_configured(std::atomic<uint64_t>& mask) {
+  const int dev = current_device();
+  if (dev < kMaxDevices) mask.fetch_or(1ull << dev, std::memory_order_release);
 }
 
 }  // namespace esmk

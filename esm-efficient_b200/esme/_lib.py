@@ -77,6 +77,7 @@ SIGNATURES = {
     'esmk_last_error': (C.c_char_p, []),
     'esmk_version': (c_int, []),
     'esmk_launch_count': (C.c_uint64, []),
+    'esmk_async_error': (c_int, []),
     'esmk_tile_capacity': (c_int, [c_int, c_int]),
     'esmk_batch_meta': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_rope_tables': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -58,6 +58,7 @@ class _Engine:
     def __init__(self, model: 'ESM2'):
         self.device = model.embed_tokens.weight.device
         self.keep: List[torch.Tensor] = []         # packed tensors the handle points into
+        self._check_storage(model)
         family = 1 if isinstance(model, ESMC) else 0
         layers = (L.LayerWeights * model.num_layers)()
         for i, layer in enumerate(model.layers):
@@ -108,6 +109,27 @@ class _Engine:
         self._layers_struct = layers
         self.workspace: Optional[torch.Tensor] = None
         self.stamp = _stamp(model)
+
+    def _check_storage(self, model):
+        """The C ABI takes raw pointers: everything it reads as bf16 must BE bf16 (model.half() / .float() would be
+        read as garbage), contiguous and on one device; quantised payloads keep their integer dtypes and fp32 scales."""
+        for name, p in list(model.named_parameters()) + list(model.named_buffers()):
+            if p.device != self.device:
+                raise RuntimeError(f'{name} lives on {p.device}, the model on {self.device}: move the whole model to one device')
+            if name.endswith('.scale') or name == 'scale':
+                ok = p.dtype == torch.float32
+                want = 'float32 (quantisation scales)'
+            elif p.dtype in (torch.uint8, torch.int8):
+                ok, want = True, ''
+            elif name.endswith('inv_freq'):
+                continue
+            else:
+                ok, want = p.dtype == torch.bfloat16, 'bfloat16'
+            if not ok:
+                raise RuntimeError(f'esme (B200 build) runs bf16 weights only: {name} is {p.dtype}, expected {want}. '
+                                   f'Do not call .half()/.float() on the model (use .to(device) / .cuda()).')
+            if not p.is_contiguous():
+                raise RuntimeError(f'{name} is not contiguous')
 
     def _weight(self, mods, qdesc, interleave=False):
         """Device pointer of the bf16 weight the GEMM reads -- the row-wise concatenation (or, for the SwiGLU
@@ -252,7 +274,8 @@ class ESM2(nn.Module):
         layers = layers or list()
         assert all(i < len(self.layers) for i in layers), \
             f'Invalid layer indices {layers}. The number of layers in the model is {len(self.layers)}.'
-        return layers
+        # the reference's loop (esme/esm.py:243-250) collects `x` when `i in layers`: ascending layer order, each once
+        return sorted(set(layers))
 
     def _packed(self, tokens, pad_args, kind, layers=(), lora_names=None):
         """Run the engine on 1-D tokens or on the packed form of 2-D tokens."""
@@ -264,6 +287,9 @@ class ESM2(nn.Module):
             assert tokens.ndim == 2, 'tokens are expected to be padded with shape (batch, seq_len, embed_dim)'
             grid = tuple(tokens.shape)
             tokens, indices, cu_lens, max_len = self._unpad(tokens)
+        pos_table = getattr(self, 'embed_positions', None)
+        if pos_table is not None and int(max_len) > pos_table.max_positions:      # esme/embedding.py:41-45, 66-70
+            raise ValueError(f'Sequence length {int(max_len)} above maximum  sequence length of {pos_table.max_positions}')
         eng = None if has_lora(self) else self.engine()      # (raises for a model that is not on a CUDA device)
         ops._need_cuda(tokens, cu_lens)
         assert tokens.dtype == torch.int64, 'tokens must be int64'
@@ -286,7 +312,6 @@ class ESM2(nn.Module):
             x = layer(x, cu_lens, max_len, lora_names)
             if i in layers:
                 reps.append(x)
-        reps = [reps[layers.index(i)] for i in layers] if layers else []
         fn = self.emb_layer_norm_after
         x = ops.layernorm(x, fn.weight, fn.bias, fn.eps)
         if kind == L.OUT_REPRESENTATION:

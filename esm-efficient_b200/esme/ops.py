@@ -22,6 +22,31 @@ def _need_cuda(*tensors):
                 'only backend and there is no CPU fallback. Move the model and inputs to a CUDA device.')
 
 
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current: the launch then goes to that device's
+    context and to ITS current stream (a process may hold models on several GPUs).  All CUDA tensor arguments
+    must live on one device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            for t in (a if isinstance(a, (tuple, list)) else (a,)):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    if dev is None:
+                        dev = t.device
+                    elif t.device != dev:
+                        raise RuntimeError(f'{fn.__name__}: tensor arguments live on different devices ({dev} and {t.device})')
+        if dev is None and isinstance(kwargs.get('device', None), (torch.device, str, int)):
+            dev = torch.device(kwargs['device']) if not isinstance(kwargs['device'], int) else torch.device('cuda', kwargs['device'])
+        if dev is None or dev.type != 'cuda' or dev == torch.device('cuda', torch.cuda.current_device()):
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -36,6 +61,7 @@ def _rows(t: torch.Tensor) -> Tuple[int, int]:
     return t2.shape[0], (t2.stride(0) if t2.shape[0] > 1 else t2.shape[1])
 
 
+@_on_tensor_device
 def batch_meta(cu_lens: torch.Tensor, T: int):
     """-> (pos int32[T], tile_info int32[capacity, 4]): per-token positions (replaces esme/rotary.py:5-14
     culen_indices) and the attention work list, one {seq start, seq length, first query row, seq id}
@@ -54,10 +80,12 @@ def rope_tables(max_len: int, head_dim: int, device) -> Tuple[torch.Tensor, torc
     cos = torch.empty(max_len, head_dim, dtype=bf16, device=device)
     sin = torch.empty_like(cos)
     _need_cuda(cos)
-    L.check(L.lib.esmk_rope_tables(cos.data_ptr(), sin.data_ptr(), max_len, head_dim, _stream()), 'esmk_rope_tables')
+    with torch.cuda.device(cos.device):
+        L.check(L.lib.esmk_rope_tables(cos.data_ptr(), sin.data_ptr(), max_len, head_dim, _stream()), 'esmk_rope_tables')
     return cos, sin
 
 
+@_on_tensor_device
 def embed(tokens: torch.Tensor, table: torch.Tensor, zero_token: int = -1,
           zero_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(tokens, table)
@@ -70,6 +98,7 @@ def embed(tokens: torch.Tensor, table: torch.Tensor, zero_token: int = -1,
     return out.reshape(*tokens.shape, table.shape[1])
 
 
+@_on_tensor_device
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
     _need_cuda(x, weight)
     assert x.dtype == bf16 and weight.dtype == bf16
@@ -82,6 +111,7 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return y
 
 
+@_on_tensor_device
 def qk_norm_rope_(q: torch.Tensor, k: torch.Tensor, H: int, head_dim: int,
                   ln_q_weight=None, ln_k_weight=None, cos=None, sin=None, pos=None):
     """In place on q and k ([T, H*hd] views sharing one row pitch)."""
@@ -97,6 +127,7 @@ def qk_norm_rope_(q: torch.Tensor, k: torch.Tensor, H: int, head_dim: int,
     return q, k
 
 
+@_on_tensor_device
 def mean_pool(x: torch.Tensor, cu_lens: torch.Tensor) -> torch.Tensor:
     """[T, D] packed rows + cu_lens int32[B+1] -> [B, D] per-sequence means (esme/pooling.py:44)."""
     _need_cuda(x, cu_lens)
@@ -109,6 +140,7 @@ def mean_pool(x: torch.Tensor, cu_lens: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def softmax(logits: torch.Tensor, log: bool) -> torch.Tensor:
     _need_cuda(logits)
     assert logits.dtype == bf16
@@ -120,6 +152,7 @@ def softmax(logits: torch.Tensor, log: bool) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            epilogue: int = L.EPI_BIAS, residual: Optional[torch.Tensor] = None, residue_scaling: float = 1.0,
            rope: Optional[tuple] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -154,6 +187,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+@_on_tensor_device
 def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torch.Tensor, max_len: int,
                 tile_info: Optional[torch.Tensor] = None, impl: int = 0) -> torch.Tensor:
     """q,k,v: [T,H,hd] views with a common row pitch (e.g. column blocks of the QKV
@@ -175,6 +209,7 @@ def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torc
     return out
 
 
+@_on_tensor_device
 def quantize(weight: torch.Tensor, bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """bf16 [N,K] weight -> (data, scale) in the library's weight-only formats (include/esmk.h):
     bits=4: uint8 [N*K/2, 1] + fp32 absmax [N*K/64];  bits=8: int8 [N,K] + fp32 [N] (row absmax / 127)."""
@@ -192,6 +227,7 @@ def quantize(weight: torch.Tensor, bits: int) -> Tuple[torch.Tensor, torch.Tenso
     return data, scale
 
 
+@_on_tensor_device
 def dequantize(data: torch.Tensor, scale: torch.Tensor, N: int, K: int, bits: int) -> torch.Tensor:
     """Inverse of `quantize`: bf16 [N,K]."""
     _need_cuda(data, scale)
@@ -202,6 +238,7 @@ def dequantize(data: torch.Tensor, scale: torch.Tensor, N: int, K: int, bits: in
     return w
 
 
+@_on_tensor_device
 def attn_pool(cls: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torch.Tensor, num_heads: int) -> torch.Tensor:
     """Class-token attention pooling (esme/pooling.py:72-136): cls [C, D], k / v [T, D] -> [B, C, D]."""
     _need_cuda(cls, k, v, cu_lens)
@@ -217,6 +254,7 @@ def attn_pool(cls: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_lens: torc
     return out
 
 
+@_on_tensor_device
 def residual_add(x: torch.Tensor, y: torch.Tensor, residue_scaling: float = 1.0) -> torch.Tensor:
     """bf(x + bf(y / residue_scaling)) (esme/attention.py:253-255 as stand-alone ops)."""
     _need_cuda(x, y)
@@ -228,6 +266,7 @@ def residual_add(x: torch.Tensor, y: torch.Tensor, residue_scaling: float = 1.0)
     return out
 
 
+@_on_tensor_device
 def add_positions_(x: torch.Tensor, table: torch.Tensor, pos: torch.Tensor, offset: int = 2) -> torch.Tensor:
     """x[t] += table[pos[t] + offset] in place, one bf16 rounding (ESM-1b / ESM-1v learned positions)."""
     _need_cuda(x, table, pos)

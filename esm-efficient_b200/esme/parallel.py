@@ -53,6 +53,39 @@ def take_sequences(tokens: torch.Tensor, cu_lens: torch.Tensor, idx: Sequence[in
     return tokens[token_index], sub_cu, int(lens.max()), token_index
 
 
+class ShardPlan:
+    """Partition of one packed batch over the ranks of `group`, built once per batch on the host: which sequences
+    each rank owns, this rank's packed sub-batch, and the row permutation that turns the all-gathered, per-rank
+    padded logits back into the original packed order.  `gather()` is the single collective of the path."""
+
+    def __init__(self, tokens: torch.Tensor, cu_lens: torch.Tensor, world: int, rank: int, embed_dim: int = 1280,
+                 device=None):
+        self.world, self.rank, self.device = world, rank, device
+        self.lengths = (cu_lens[1:] - cu_lens[:-1]).tolist()
+        self.owned = partition_sequences(self.lengths, world, embed_dim)
+        self.shares = [take_sequences(tokens, cu_lens, o) for o in self.owned]
+        self.t_max = max(int(s[3].numel()) for s in self.shares)
+        self.T = int(cu_lens[-1])
+        self.tokens, self.cu_lens, self.max_len, self.token_index = self.shares[rank]
+        self.imbalance = imbalance(self.lengths, self.owned, embed_dim)
+        # perm[t] = row of the gathered [world * t_max, width] buffer holding packed token t
+        perm = torch.empty(self.T, dtype=torch.int64)
+        for r, s in enumerate(self.shares):
+            perm[s[3]] = torch.arange(s[3].numel(), dtype=torch.int64) + r * self.t_max
+        self.perm = perm.to(device)
+        self._local = self._gathered = None
+
+    def gather(self, out: torch.Tensor, group=None) -> torch.Tensor:
+        """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank."""
+        width = out.shape[1]
+        if self._local is None or self._local.shape[1] != width or self._local.dtype != out.dtype:
+            self._local = torch.zeros(self.t_max, width, dtype=out.dtype, device=self.device)
+            self._gathered = torch.empty(self.world * self.t_max, width, dtype=out.dtype, device=self.device)
+        self._local[:out.shape[0]] = out
+        dist.all_gather_into_tensor(self._gathered, self._local, group=group)      # the only collective of the path
+        return self._gathered.index_select(0, self.perm)
+
+
 def sharded_forward(fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor], tokens: torch.Tensor,
                     cu_lens: torch.Tensor, width: int, embed_dim: int = 1280, group=None,
                     device=None, dtype=torch.bfloat16) -> torch.Tensor:
@@ -61,25 +94,12 @@ def sharded_forward(fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor
     the original packed order: returns [T, width] on every rank.
 
     tokens / cu_lens are the FULL batch as host tensors, identical on every rank."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    lengths = (cu_lens[1:] - cu_lens[:-1]).tolist()
-    owned = partition_sequences(lengths, world, embed_dim)
-    shares = [take_sequences(tokens, cu_lens, o) for o in owned]
-    t_max = max(int(s[3].numel()) for s in shares)
-    tok_r, cu_r, max_len_r, _ = shares[rank]
-    local = torch.zeros(t_max, width, dtype=dtype, device=device)
-    if tok_r.numel() > 0:
-        out = fn(tok_r.to(device), cu_r.to(device), max_len_r)
-        local[:out.shape[0]] = out
-    gathered = torch.empty(world * t_max, width, dtype=dtype, device=device)
-    dist.all_gather_into_tensor(gathered, local, group=group)      # the only collective of the path
-    T = int(cu_lens[-1])
-    src = torch.cat([s[3].new_tensor(range(s[3].numel())) + r * t_max for r, s in enumerate(shares)])
-    dst = torch.cat([s[3] for s in shares])
-    result = torch.empty(T, width, dtype=dtype, device=device)
-    result[dst.to(device)] = gathered[src.to(device)]
-    return result
+    plan = ShardPlan(tokens, cu_lens, dist.get_world_size(group), dist.get_rank(group), embed_dim, device)
+    if plan.tokens.numel() > 0:
+        out = fn(plan.tokens.to(device), plan.cu_lens.to(device), plan.max_len)
+    else:
+        out = torch.zeros(0, width, dtype=dtype, device=device)
+    return plan.gather(out, group)
 
 
 def model_sharded_forward(model, tokens, cu_lens, kind: str = 'logits', group=None):

@@ -33,6 +33,15 @@ class _QuantLinear(nn.Module):
         self.register_buffer('scale', scale)
         self.bias = None if bias is None else nn.Parameter(bias.detach().clone(), requires_grad=False)
 
+    def _apply(self, fn, *a, **kw):
+        """Device moves apply; dtype casts (model.bfloat16(), .to(torch.bfloat16)) must not touch the integer payload
+        (torch leaves integer tensors alone) NOR the fp32 block scales, which the kernels read as fp32."""
+        scale = self.scale
+        out = super()._apply(fn, *a, **kw)
+        if self.scale.dtype != torch.float32:
+            self.scale = scale.to(self.scale.device)
+        return out
+
     @classmethod
     def from_linear(cls, linear: nn.Linear) -> '_QuantLinear':
         """Quantise an nn.Linear whose bf16 weight already lives on a CUDA device."""

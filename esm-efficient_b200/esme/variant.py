@@ -17,6 +17,7 @@ import torch
 
 from . import _lib as L
 from .alphabet import Alphabet3, tokenize
+from .lora import has_lora
 
 
 class MaskMarginDataset(torch.utils.data.Dataset):
@@ -73,7 +74,10 @@ def _masked_position_log_probs(model, ds: MaskMarginDataset, batch_size: int) ->
             cu = torch.arange(0, (b1 - b0 + 1) * width, width, dtype=torch.int32, device=device)
             z = model.forward_representation(rows.reshape(-1), (cu, width))          # packed, no padding
             masked_rows = z[torch.arange(b1 - b0, device=device) * width + local[b0:b1]]
-            out.append(model.engine().lm_head(masked_rows.contiguous(), L.OUT_LOG_PROB))
+            masked_rows = masked_rows.contiguous()
+            # (a model with LoRA adapters runs the operator path: its engine cannot be built over LoRA-wrapped linears)
+            out.append(model._lm_head_ops(masked_rows, L.OUT_LOG_PROB) if has_lora(model)
+                       else model.engine().lm_head(masked_rows, L.OUT_LOG_PROB))
     return torch.cat(out)
 
 

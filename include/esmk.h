@@ -37,6 +37,13 @@ typedef void* esmk_stream_t; /* cudaStream_t */
 /* ---- library ----------------------------------------------------------- */
 ESMK_API const char* esmk_last_error(void);
 ESMK_API int esmk_version(void);
+/* Device-detected data errors.  Kernels cannot return a status, so invalid DATA met on the device (a token id outside
+ * the embedding table -- the reference would trip a device-side assert in F.embedding, esme/esm.py:187 -- or a
+ * sequence longer than the learned positional table, esme/embedding.py) sets a sticky flag that makes the NEXT entry
+ * point called after the kernel ran fail with a message naming the cause (the flag is then cleared).
+ * esmk_async_error() polls and clears it explicitly: 0 or a bit-or of the codes below. */
+enum esmk_async_code { ESMK_ASYNC_BAD_TOKEN = 1, ESMK_ASYNC_BAD_POSITION = 2 };
+ESMK_API int esmk_async_error(void);
 /* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
 ESMK_API uint64_t esmk_launch_count(void);
 
@@ -121,7 +128,7 @@ typedef struct {
   const void* rope_cos; /* bf16 [max_len, hd] */
   const void* rope_sin;
   const int32_t* pos;   /* int32 [M] */
-  int head_dim;         /* 16, 32, 64 or 128 */
+  int head_dim;         /* 16, 32 or 64 (other head dims: ESMK_EPI_BIAS + esmk_qk_norm_rope) */
   int rope_cols;        /* columns [0, rope_cols) are rotated (= 2*D) */
 } esmk_gemm_args;
 

@@ -85,3 +85,26 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert n == len(syms)
     assert (gemm, cfg, layer, weights, qw) == (C.sizeof(_lib.GemmArgs), C.sizeof(_lib.Config), C.sizeof(_lib.LayerWeights),
                                                C.sizeof(_lib.Weights), C.sizeof(_lib.QWeight))
+
+
+def test_integration_md_config_struct_matches_header():
+    """The ctypes `_Cfg` snippet of INTEGRATION.md B3 must list exactly the fields of `esmk_config` (a maintainer
+    copying a short struct would hand the library garbage in the trailing fields)."""
+    import re
+    header = open(os.path.join(ROOT, 'include', 'esmk.h')).read()
+    body = re.search(r'typedef struct \{([^}]*)\} esmk_config;', header, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if decl:
+            ctype, names = decl.split(None, 1)
+            fields += [(n.strip(), ctype) for n in names.split(',')]
+    md = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    snippet = md[md.index('class _Cfg(ctypes.Structure)'):]
+    snippet = snippet[:snippet.index('\n# fill')]
+    names = re.findall(r"'(\w+)'", snippet)
+    assert names == [n for n, _ in fields], (names, fields)
+    assert [n for n, t in fields if t == 'float'] == ['residue_scaling'] and "('residue_scaling', ctypes.c_float)" in snippet
+    from esme import _lib
+    assert [n for n, _ in _lib.Config._fields_] == names
