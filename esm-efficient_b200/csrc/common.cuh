@@ -184,6 +184,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe: try_wait may suspend the thread for a system-dependent time when the phase is still pending,
+// which starves the OTHER barriers a multi-barrier poll loop is watching; test_wait returns at once.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug traps (-> launch failure reported by the host)
 // instead of hanging the GPU box.
 #ifndef ESMK_WAIT_TIMEOUT_NS
@@ -371,6 +384,22 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       :
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// Whole-warp variants: every lane executes the call (operands are warp-uniform and stay in uniform registers), one
+// elected lane issues.  In a lane-predicated region (`if (lane == 0)`) the compiler has to re-broadcast every operand
+// into uniform registers before each tcgen05 instruction (ELECT + 5 x R2UR.BROADCAST per MMA in the SASS), which made a
+// block's 8 MMAs + 4 commits cost ~1,800 cycles.
+__device__ __forceinline__ void umma_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (elect_one()) umma_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (elect_one()) umma_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1).

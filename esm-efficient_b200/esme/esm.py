@@ -251,6 +251,11 @@ class ESM2(nn.Module):
         self._engine = None
         return super()._apply(fn, *a, **kw)
 
+    def __getstate__(self):                # copy.deepcopy / pickle: the engine (ctypes handle) is rebuilt on demand
+        state = self.__dict__.copy()
+        state['_engine'] = None
+        return state
+
     # ---- reference API -------------------------------------------------------
     def embedding(self, tokens, pad_args=None):
         """esme/esm.py:176-199."""

@@ -58,8 +58,11 @@ def test_engine_rejects_non_bf16_storage():
     g = load_golden('esm2_tiny.npz')
     tokens, cu, max_len = g['tokens'].to(DEV), g['cu_lens'].to(DEV), g['max_len']
     want = model(tokens, (cu, max_len))
+    import copy
     with pytest.raises(RuntimeError, match='bf16 weights only'):
-        model.half()(tokens, (cu, max_len))
+        copy.deepcopy(model).half()(tokens, (cu, max_len))
+    with pytest.raises(RuntimeError, match='bf16 weights only'):
+        copy.deepcopy(model).float()(tokens, (cu, max_len))
     assert torch.equal(model.bfloat16()(tokens, (cu, max_len)), want)
     q = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors', quantization='4bit', device=DEV)
     y = q(tokens, (cu, max_len))
