@@ -21,13 +21,12 @@ sys.path.insert(0, os.path.join(ROOT, 'esm-efficient_b200'))
 
 CONFIGS = [
     {'ESMK_ATTN_IMPL': 'v1'},
-    {'ESMK_ATTN_IMPL': 'v3'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_RESCALE_THRESHOLD': '1'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_RESCALE_THRESHOLD': '8'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_POLY': '2'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_POLY': '3'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_HEADS_PER_CTA': '1'},
-    {'ESMK_ATTN_IMPL': 'v3', 'ESMK_ATTN_HEADS_PER_CTA': '2'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '1'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '2'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '3'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_VARIANT': '0'},
+    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_VARIANT': '2'},
 ]
 
 
