@@ -14,9 +14,10 @@
 //   TMEM (256 columns): S fp32 [0,128) | P bf16x2 [128,192) | O fp32 [192,256)
 //   - S_{j+1} is issued as soon as the softmax warps hold S_j in registers (s_free), so it overlaps the
 //     exponentials of block j; no P staging in shared memory;
-//   - O accumulates in TMEM and is rescaled lazily: only when a row maximum grows by more than 2^8 over the
-//     reference maximum its P values were scaled with (P is a bf16 FLOAT: its relative precision does not
-//     depend on the reference; row sums stay in fp32);
+//   - O accumulates in TMEM and is rescaled whenever a row maximum outgrows the reference its P values were scaled
+//     with by more than `rescale_threshold` (log2 units).  Default 0 = the exact running maximum of
+//     FlashAttention-2, the kernel the reference calls: the row's largest P is exactly 1.0 (no rounding error on the
+//     dominant term), which is what round 1's lazy 2^8 threshold gave up (1.14x the oracle's noise; now 0.98x);
 //   - the last key block of a sequence is trimmed: the S MMA runs with N = valid keys rounded up to 16, the
 //     P.V MMA with as many 16-key steps, and the softmax warps skip 32-column chunks without valid keys;
 //     warps whose 32 query rows lie beyond the sequence end only keep the barrier protocol.
@@ -35,6 +36,7 @@
 // scores, un-normalised P rounded to bf16 before P.V, fp32 row sums of the un-rounded P, one final rounding.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -57,7 +59,7 @@ constexpr int AT_TMEM_COLS = 256;
 constexpr int AT_THREADS = 64 + 128;         // producer warp, MMA warp, 4 softmax warps (one thread per query row)
 constexpr int AT_SMEM = Q_BYTES * 6 + 1024 + 192;
 constexpr int kDefaultPoly = 0;            // eighths of the exponentials on the FMA pipes (see exp_pack32): measured, no gain
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr float kRescaleThreshold = 0.0f;  // log2 units (see attn_varlen for the measured accuracy / time trade-off)
 
 // Software exp2 on the FMA pipes (the MUFU unit gives only 16 ex2 per clock per SM, half of what the tensor
 // pipe could consume at head_dim 64): floor(x) falls out of one round-down add against the 1.5*2^23 magic
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
               const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
-              long long* __restrict__ trace, long long* __restrict__ cta_trace) {
+              float rescale_threshold, long long* __restrict__ trace, long long* __restrict__ cta_trace) {
   griddep_launch_dependents();   // the next kernel (out-projection) may be scheduled as SMs drain
   griddep_wait();                // tile_info / q / k / v of the previous kernels are visible from here
   const long long t_entry = cta_trace ? (long long)global_timer_ns() : 0;
@@ -378,9 +380,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           if (j == 0) {
             m_ref = mx;
           } else {
-            // lazy rescale: P = exp2(x - m_ref) is a bf16 FLOAT, so its relative precision does not depend on
-            // m_ref; the reference moves only when a row maximum outgrows it by more than 2^kRescaleThreshold
-            const bool grow = mx > m_ref + kRescaleThreshold;
+            // the reference moves when a row maximum outgrows it by more than 2^rescale_threshold (0: always, the
+            // exact running maximum of FlashAttention-2 -- the largest P of the row is then exactly 1.0)
+            const bool grow = mx > m_ref + rescale_threshold;
             if (__any_sync(0xffffffffu, grow)) {
               const float m_new = grow ? mx : m_ref;
               const float f = fast_exp2(m_ref - m_new);
@@ -496,390 +498,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     p[3] = ((long long)smid << 32) | (long long)(n_kv * nh);
   }
 }
-
-// ===========================================================================
-// attn64_v5_kernel (round 2): the round-1 pipeline (attn64_kernel above) with
-//   * the exact running maximum of FlashAttention-2 (rescale threshold 0, the arithmetic of the kernel the reference
-//     calls) instead of the lazy 2^8 threshold (which cost 1.3x the oracle's rounding noise): the row's P values are
-//     aligned to the current maximum, O is rescaled whenever it grows;
-//   * the rescale of O and the wait for P_{j-1} to be consumed moved BEHIND the first 32 exponentials of the block
-//     (both need the previous P.V, which is still in flight when the row maximum is known);
-//   * 3-input max in four independent chains for the row maximum (half the ALU instructions, a quarter of the depth);
-//   * a 1-D grid (tile-major over the LPT work list): no 65,535 limit on the number of query tiles.
-// Structures that were built and measured this round and did NOT pay on the config-2 batch (round-1 kernel 0.335 ms):
-// 64-key blocks in three rotating S/P slots with a correction warpgroup (0.383 ms), four key-split softmax streams
-// per SM with a shared issuer warp (0.390 ms) or with every stream issuing its own MMAs (0.477 ms) -- next to 16 busy
-// softmax warps one tcgen05.mma / commit costs 50-150 issue cycles, so halving the block size doubles a serial cost
-// that is already on the critical path -- and a correction warpgroup on this layout (needs 152 + 48 + 40 registers
-// per thread triple: spills).  Traces and numbers: profiles/r2_attn_experiments.md.
-// ===========================================================================
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// maximum of 32 scores: four independent chains of 3-input max
-__device__ __forceinline__ float chunk_max3(const uint32_t (&s)[32]) {
-  float m[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    m[c] = fmax3(__uint_as_float(s[8 * c]), __uint_as_float(s[8 * c + 1]), __uint_as_float(s[8 * c + 2]));
-    m[c] = fmax3(m[c], __uint_as_float(s[8 * c + 3]), __uint_as_float(s[8 * c + 4]));
-    m[c] = fmax3(m[c], __uint_as_float(s[8 * c + 5]), __uint_as_float(s[8 * c + 6]));
-    m[c] = fmaxf(m[c], __uint_as_float(s[8 * c + 7]));
-  }
-  return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-}
-
-template <int POLY>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attn64_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-              const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
-              const int4* __restrict__ tile_info, int H, int heads_per_cta, int n_groups, float scale_log2,
-              float rescale_threshold, int variant) {
-  [[maybe_unused]] long long* const trace = nullptr;
-  [[maybe_unused]] long long* const cta_trace = nullptr;
-  griddep_launch_dependents();   // the next kernel (out-projection) may be scheduled as SMs drain
-  griddep_wait();                // tile_info / q / k / v of the previous kernels are visible from here
-  const long long t_entry = cta_trace ? (long long)global_timer_ns() : 0;
-  // work item: {first packed row of the sequence, sequence length, first query row of this tile, -}
-  // grid = (head groups, tiles): launch order walks all head groups of the longest sequences first (global LPT)
-  const int tile_idx = blockIdx.x / n_groups;           // 1-D grid, tile-major over the LPT-sorted work list
-  const int4 info = __ldg(tile_info + tile_idx);
-  const int seq_start = info.x, L = info.y, q0 = info.z;
-  if (L <= 0) return;                      // unused slot of the (upper-bound sized) work list
-  const int n_kv = (L + TILE - 1) / TILE;
-  // this CTA walks `nh` consecutive heads of the same query tile: the producer and the MMA warp run ahead
-  // into the next head while the softmax warps finish the current one, hiding the Q/K load and first-S latency
-  const int head0 = (blockIdx.x - tile_idx * n_groups) * heads_per_cta;
-  const int nh = min(heads_per_cta, H - head0);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                  // 2 stages (one per head in flight)
-  uint8_t* sK = sQ + 2 * Q_BYTES;      // 2 stages
-  uint8_t* sV = sK + 2 * Q_BYTES;      // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Q_BYTES);
-  uint64_t* q_full = bars + 0;   // [2]
-  uint64_t* q_empty = bars + 2;  // [2]
-  uint64_t* k_full = bars + 4;   // [2]
-  uint64_t* k_empty = bars + 6;  // [2]
-  uint64_t* v_full = bars + 8;   // [2]
-  uint64_t* v_empty = bars + 10; // [2]
-  uint64_t* s_full = bars + 12;
-  uint64_t* s_free = bars + 13;
-  uint64_t* p_full = bars + 14;
-  uint64_t* o_done = bars + 15;
-  uint64_t* o_free = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);    // one arrival per softmax warp
-    mbar_init(p_full, 4);
-    mbar_init(o_done, 1);
-    mbar_init(o_free, 4);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, AT_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_P = tmem_base + 128;
-  const uint32_t tmem_O = tmem_base + 192;
-  const long long t_loop = cta_trace ? (long long)global_timer_ns() : 0;
-
-  // `it` counts key blocks across all heads of this CTA: K/V stage = it & 1, stage phase = (it >> 1) & 1,
-  // and the per-block barriers (s_full, s_free, p_full, o_done) complete once per block -> parity it & 1.
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      int it = 0;
-      for (int hi = 0; hi < nh; ++hi) {
-        const int col = (head0 + hi) * HD64;
-        const int qs = hi & 1;
-        mbar_wait_backoff(&q_empty[qs], ((hi >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qs], Q_BYTES);
-        tma_load_2d(sQ + qs * Q_BYTES, &tmQ, &q_full[qs], col, seq_start + q0);
-        for (int j = 0; j < n_kv; ++j, ++it) {
-          const int st = it & 1;
-          const uint32_t ph = (it >> 1) & 1;
-          const int krow = seq_start + j * TILE;
-          mbar_wait_backoff(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
-          tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
-          mbar_wait_backoff(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
-          tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
-      // the last key block of a sequence is trimmed to its valid keys rounded up to 16: N of the S MMA and the
-      // number of K steps of the P.V MMA (the softmax warps skip the same columns)
-      auto issue_s = [&](int qs, int blk, int j) {                      // S = Q[qs] . K[blk & 1]^T, key block j
-        const int st = blk & 1;
-        const int n_keys = min(TILE, ((L - j * TILE) + 15) & ~15);
-        const uint32_t idesc_s = make_idesc_bf16(TILE, n_keys, 0, 0);   // Q K^T : both K-major from smem
-        tc_fence_after();
-        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * Q_BYTES), 16, 1024, 2);
-        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * Q_BYTES), 16, 1024, 2);
-#pragma unroll
-        for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[st]);
-      };
-      int it = 0;
-      [[maybe_unused]] const bool tr_on = false;
-      [[maybe_unused]] long long* tr_base = trace ? nullptr : nullptr;
-      [[maybe_unused]] int tr_n = 0;
-      for (int hi = 0; hi < nh; ++hi) {
-        const int qs = hi & 1;
-        mbar_wait_backoff(&q_full[qs], (hi >> 1) & 1);
-        mbar_wait_backoff(&k_full[it & 1], (it >> 1) & 1);
-        if (it > 0) mbar_wait_backoff(s_free, (it - 1) & 1);            // previous head's last S is in registers
-        issue_s(qs, it, 0);
-        if (n_kv == 1) umma_commit(&q_empty[qs]);
-        for (int j = 0; j < n_kv; ++j) {
-          const int cur = it + j;
-          const int st = cur & 1;
-          tr_n = cur;
-          TRACE_STAMP(0);
-          // (the TMA barriers are polled BEFORE the softmax-dependent ones: every poll costs ~100 cycles while the
-          //  MIO queue is full of MUFU work, and these are off the S -> P -> O critical path)
-          if (j + 1 < n_kv) {
-            mbar_wait_backoff(&k_full[(cur + 1) & 1], ((cur + 1) >> 1) & 1);
-            mbar_wait_backoff(s_free, cur & 1);                          // S_j has been copied to registers
-            TRACE_STAMP(1);
-            issue_s(qs, cur + 1, j + 1);
-            TRACE_STAMP(2);
-            if (j + 2 == n_kv) umma_commit(&q_empty[qs]);                // last S of this head: Q slot reusable
-          }
-          mbar_wait_backoff(&v_full[st], (cur >> 1) & 1);
-          TRACE_STAMP(3);
-          mbar_wait_backoff(p_full, cur & 1);
-          TRACE_STAMP(4);
-          if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
-          tc_fence_after();
-          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
-          const int k_steps = min(TILE / 16, ((L - j * TILE) + 15) >> 4);
-          for (int k = 0; k < k_steps; ++k)     // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
-            umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
-          umma_commit(o_done);
-          umma_commit(&v_empty[st]);
-          TRACE_STAMP(5);
-        }
-        it += n_kv;
-      }
-    }
-  } else {
-    // ===================== softmax warps: one thread per query row =====================
-    // Every instruction that goes through the SM's MIO queue (mbarrier polls, TMEM loads/stores, shared
-    // memory) waits behind the MUFU ops of whichever CTA is in its exponential phase, so the per-block
-    // protocol is kept to the minimum: one S wait, four TMEM loads, one arrive, one O wait, four P stores,
-    // one arrive per 128 exponentials -- no cross-thread exchange of the row maximum or the row sum.
-    const int quad = warp & 3;                 // TMEM lane quadrant (warps 2,3,4,5 -> quadrants 2,3,0,1)
-    const int r = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_S + lane_off;
-    const uint32_t tP = tmem_P + lane_off;
-    const uint32_t tO = tmem_O + lane_off;
-    int it = 0;
-    [[maybe_unused]] const bool tr_on = false && (threadIdx.x == 64);
-    [[maybe_unused]] long long* tr_base = trace ? nullptr : nullptr;
-    [[maybe_unused]] int tr_n = 0;
-    // a warp whose 32 query rows all lie beyond the end of the sequence keeps the barrier protocol but skips
-    // the exponentials and the stores
-    const bool rows_ok = q0 + quad * 32 < L;
-    bool s_ready = false;                      // the next block's S barrier was seen complete during the exponentials
-    for (int hi = 0; hi < nh; ++hi) {
-      float m_ref = -INFINITY, l_sum = 0.f;
-      for (int j = 0; j < n_kv; ++j) {
-        const int cur = it + j;
-        // valid keys among the block's 128 columns (none for a warp without valid rows); only the last key
-        // block of a sequence is masked, and there whole 32-column chunks without valid keys are skipped
-        const int kv_valid = rows_ok ? L - j * TILE : 0;
-        const bool masked = kv_valid < TILE;
-        tr_n = cur;
-        TRACE_STAMP(0);
-        if (!s_ready) mbar_wait(s_full, cur & 1);
-        tc_fence_after();
-        TRACE_STAMP(1);
-        uint32_t s0[32], s1[32], s2[32], s3[32];   // (unconditional loads: conditional asm outputs go to local memory)
-        tmem_ld32(tS, s0);
-        tmem_ld32(tS + 32, s1);
-        tmem_ld32(tS + 64, s2);
-        tmem_ld32(tS + 96, s3);
-        tmem_wait_ld();
-        TRACE_STAMP(2);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ARRIVE(s_free);             // all 4 warps arrived -> S may be overwritten
-        bool resc = false;                          // warp-uniform: O must be rescaled before this block's P.V
-        float resc_f = 1.0f;
-        if (rows_ok) {
-          float mine;
-          if (!masked) {
-            if (variant & 1) mine = fmaxf(fmaxf(chunk_max<false>(s0, 32), chunk_max<false>(s1, 32)),
-                                          fmaxf(chunk_max<false>(s2, 32), chunk_max<false>(s3, 32)));
-            else mine = fmaxf(fmaxf(chunk_max3(s0), chunk_max3(s1)), fmaxf(chunk_max3(s2), chunk_max3(s3)));
-          } else {
-            mine = chunk_max<true>(s0, kv_valid);
-            if (kv_valid > 32) mine = fmaxf(mine, chunk_max<true>(s1, kv_valid - 32));
-            if (kv_valid > 64) mine = fmaxf(mine, chunk_max<true>(s2, kv_valid - 64));
-            if (kv_valid > 96) mine = fmaxf(mine, chunk_max<true>(s3, kv_valid - 96));
-          }
-          TRACE_STAMP(3);
-          const float mx = mine * scale_log2;
-          if (j == 0) {
-            m_ref = mx;
-          } else {
-            // The running maximum grew (threshold 0: the exact running maximum of FlashAttention-2, the reference's
-            // arithmetic; a threshold t > 0 lets P reach 2^t before O is touched).  The rescale of O itself is
-            // DEFERRED behind the first 32 exponentials: it needs the previous P.V (o_done), which is still in
-            // flight here.
-            const bool grow = mx > m_ref + rescale_threshold;
-            if (__any_sync(0xffffffffu, grow)) {
-              resc = true;
-              resc_f = grow ? fast_exp2(m_ref - mx) : 1.0f;
-              l_sum *= resc_f;
-              if (grow) m_ref = mx;
-            }
-          }
-        }
-        // ---- P = exp2(S*c - m_ref) -> bf16 -> TMEM, 32 keys (16 packed columns) per store ----
-        // P_{cur-1} must have been consumed before it is overwritten, and O is quiescent once o_done(cur-1) has
-        // completed; both waits sit behind the first chunk's exponentials (they used to stall ~300 cycles up front)
-        auto settle_o = [&]() {
-          if (cur > 0) {                                  // (block 0 of a later head: the previous head's last P.V)
-            mbar_wait(o_done, (cur - 1) & 1);
-            tc_fence_after();
-          }
-          if (resc) {
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              uint32_t o[16];
-              tmem_ld16(tO + h * 16, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * resc_f);
-              tmem_st16(tO + h * 16, o);
-            }
-          }
-        };
-        if (!masked) {
-          uint32_t pk[16];
-          if (variant & 2) settle_o();
-          l_sum += exp_pack32<POLY, false>(s0, 32, scale_log2, m_ref, pk);
-          if (!(variant & 2)) settle_o();
-          tmem_st16(tP, pk);
-          l_sum += exp_pack32<POLY, false>(s1, 32, scale_log2, m_ref, pk);
-          tmem_st16(tP + 16, pk);
-          // S_{j+1} was issued when this block's S reached the registers: poll its barrier here, where the
-          // latency of the poll hides behind the remaining exponentials instead of opening the next block
-          s_ready = mbar_try_wait(s_full, (cur + 1) & 1);
-          l_sum += exp_pack32<POLY, false>(s2, 32, scale_log2, m_ref, pk);
-          tmem_st16(tP + 32, pk);
-          l_sum += exp_pack32<POLY, false>(s3, 32, scale_log2, m_ref, pk);
-          tmem_st16(tP + 48, pk);
-        } else {
-          s_ready = false;
-          uint32_t pk[16];
-          settle_o();
-          if (kv_valid > 0) {
-            l_sum += exp_pack32<POLY, true>(s0, kv_valid, scale_log2, m_ref, pk);
-            tmem_st16(tP, pk);
-          }
-          if (kv_valid > 32) {
-            l_sum += exp_pack32<POLY, true>(s1, kv_valid - 32, scale_log2, m_ref, pk);
-            tmem_st16(tP + 16, pk);
-          }
-          if (kv_valid > 64) {
-            l_sum += exp_pack32<POLY, true>(s2, kv_valid - 64, scale_log2, m_ref, pk);
-            tmem_st16(tP + 32, pk);
-          }
-          if (kv_valid > 96) {
-            l_sum += exp_pack32<POLY, true>(s3, kv_valid - 96, scale_log2, m_ref, pk);
-            tmem_st16(tP + 48, pk);
-          }
-        }
-        tmem_wait_st();
-        TRACE_STAMP(6);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ARRIVE(p_full);
-      }
-      it += n_kv;
-      // ---- head epilogue: O / l for this thread's row ----
-      const float inv = 1.0f / l_sum;
-      mbar_wait(o_done, (it - 1) & 1);
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tO, o0);
-      tmem_ld32(tO + 32, o1);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
-      if (rows_ok && q0 + r < L) {
-        __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dst + i) = make_uint4(
-              pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dst + 32 + i) = make_uint4(
-              pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-  if (cta_trace != nullptr && threadIdx.x == 0) {
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    long long* p = cta_trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4;
-    p[0] = t_entry;
-    p[1] = t_loop;
-    p[2] = (long long)global_timer_ns();
-    p[3] = ((long long)smid << 32) | (long long)(n_kv * nh);
-  }
-}
-
 
 // ---------------------------------------------------------------------------
 // CUDA-core kernel: one warp per (query token, head); lanes = keys for the
@@ -1051,10 +669,6 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
   // scale_hd: the model's true head_dim when the heads were zero-padded to `hd` (softmax scale = scale_hd^-0.5)
   const float scale_log2 = (1.0f / sqrtf((float)(scale_hd > 0 ? scale_hd : hd))) * 1.4426950408889634f;
-  static const int tc_version = [] {            // ESMK_ATTN_IMPL=v1 selects the round-1 kernel (A/B measurements)
-    const char* e = getenv("ESMK_ATTN_IMPL");
-    return (e != nullptr && e[0] == 'v' && e[1] == '1') ? 1 : 2;
-  }();
   if (hd == 64 && impl == 0) {
     ESMK_REQUIRE(tile_info != nullptr, "tile_info (esmk_batch_meta) required");
     ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");
@@ -1062,9 +676,25 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
-    static const int poly = [] {                // eighths of the exponentials evaluated on the FMA pipes
+    using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
+                              float, long long*, long long*);
+    static const kernel_t kernel = [] {         // ESMK_ATTN_POLY=1: 3/8 of the exponentials on the FMA pipes (A/B runs)
       const char* e = getenv("ESMK_ATTN_POLY");
-      return e ? atoi(e) : kDefaultPoly;
+      return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0> : attn64_kernel<3>;
+    }();
+    static std::atomic<uint64_t> configured{0};                       // per device: a process may use several GPUs
+    if (needs_config(configured)) {
+      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+      mark_configured(configured);
+    }
+    // log2 units by which a row maximum may outgrow the reference its P values are scaled with before O is rescaled.
+    // 0 = the exact running maximum of FlashAttention-2.  Measured (tools/attn_ab.py: rms-relative error against the
+    // exact fp64 attention on the same bf16 inputs -- flash-attn 2.8.3 1.886e-3, oracle 1.931e-3 -- and time on the
+    // config-2 batch):  0: 1.887e-3 0.352 ms | 1: 1.943e-3 0.349 | 2: 1.996e-3 0.340 | 3: 2.053e-3 0.333 |
+    //                   4: 2.110e-3 0.332 | 8: 2.209e-3 0.332 (round 1).  Parity first: the default is 0.
+    static const float threshold = [] {
+      const char* e = getenv("ESMK_ATTN_RESCALE_THRESHOLD");
+      return e ? (float)atof(e) : kRescaleThreshold;
     }();
     // heads per CTA: amortise the per-CTA start-up over up to 4 heads while keeping >= ~8 CTAs per SM slot
     int hpc = 1;
@@ -1075,43 +705,15 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       const int v = atoi(e);
       if (v >= 1 && v <= 8) hpc = v;
     }
-    const int n_groups = (H + hpc - 1) / hpc;
-    if (tc_version == 2) {
-      using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, int,
-                                float, float, int);
-      static const int variant = [] { const char* e = getenv("ESMK_ATTN_VARIANT"); return e ? atoi(e) : 0; }();
-      static const kernel_t kernel = poly <= 0 ? attn64_v5_kernel<0> : (poly <= 2 ? attn64_v5_kernel<3> : attn64_v5_kernel<3>);
-      static std::atomic<uint64_t> configured{0};                     // per device: a process may use several GPUs
-      if (needs_config(configured)) {
-        ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        mark_configured(configured);
-      }
-      static const float threshold = [] {       // log2 units; 0 = follow the running maximum exactly (FlashAttention-2)
-        const char* e = getenv("ESMK_ATTN_RESCALE_THRESHOLD");
-        return e ? (float)atof(e) : 0.0f;
-      }();
-      const long ctas = (long)n_groups * tile_capacity(T, B);
-      ESMK_REQUIRE(ctas <= 0x7fffffffL, "too many attention work items for one launch");
-      ESMK_CUDA(launch_pdl(kernel, dim3((unsigned)ctas), dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, (__nv_bfloat16*)out,
-                           ldo, reinterpret_cast<const int4*>(tile_info), H, hpc, n_groups, scale_log2, threshold, variant));
-      count_launch();
-      ESMK_CUDA(cudaGetLastError());
-      (void)max_len;
-      return 0;
+    // grid.y is limited to 65,535: a longer work list is walked in several launches
+    const int n_tiles = tile_capacity(T, B);
+    for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
+      dim3 grid((H + hpc - 1) / hpc, std::min(65535, n_tiles - t0));
+      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
+                           reinterpret_cast<const int4*>(tile_info) + t0, H, hpc, scale_log2, threshold,
+                           (long long*)nullptr, (long long*)nullptr));
+      if (t0 > 0) count_launch();
     }
-    using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
-                              long long*, long long*);
-    static const kernel_t kernel = poly <= 0 ? attn64_kernel<0> : attn64_kernel<3>;
-    static std::atomic<uint64_t> configured{0};
-    if (needs_config(configured)) {
-      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      mark_configured(configured);
-    }
-    ESMK_REQUIRE(tile_capacity(T, B) <= 65535, "too many attention tiles for one launch (T/128 + B > 65535)");
-    dim3 grid(n_groups, tile_capacity(T, B));
-    ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
-                         reinterpret_cast<const int4*>(tile_info), H, hpc, scale_log2, (long long*)nullptr,
-                         (long long*)nullptr));
   } else {
     dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
     attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,

@@ -60,15 +60,17 @@ def test_attention_tcgen05_kernel():
 
 def test_attention_noise_against_exact_result():
     """Distance from the exact (fp64) attention on the same bf16 inputs, next to the oracle's bf16 restatement of
-    flash-attn.  The tcgen05 kernel keeps the FIRST key block's row maximum as the softmax reference (lazy
-    rescale); flash-attn tracks the running maximum, which puts the mantissas of the dominant P values just below
-    a power of two where bf16 rounds best.  That is worth a factor ~1.2 in P-rounding noise (reproduced on the
-    CPU in DESIGN.md 4.2), so the bound is 1.3 x the oracle's distance, and the generic kernel must match it."""
+    flash-attn and the flash-attn wheel itself (the kernel the reference calls).  The tcgen05 kernel follows the
+    running row maximum exactly (rescale threshold 0, FlashAttention-2's arithmetic: the largest P of a row is
+    exactly 1.0), so it must sit at the oracle's / flash-attn's own distance: bound 1.05 x (round 1's lazy 2^8
+    threshold needed 1.3 x; the threshold sweep is recorded in csrc/attn.cu and profiles/r2_attn_experiments.md)."""
     out = D.attn_accuracy()
     floor = out['oracle_bf16']['rms_rel']
     assert out['exact_rounded_to_bf16']['rms_rel'] <= floor
     assert out['generic']['rms_rel'] <= 1.05 * floor, out
-    assert out['tcgen05']['rms_rel'] <= 1.3 * floor, out
+    assert out['tcgen05']['rms_rel'] <= 1.05 * floor, out
+    if 'flash_attn_library' in out:
+        assert out['tcgen05']['rms_rel'] <= 1.05 * out['flash_attn_library']['rms_rel'], out
     assert out['tcgen05']['max_rel_to_peak'] <= 6e-3, out
 
 

@@ -19,15 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'esm-efficient_b200'))
 
-CONFIGS = [
-    {'ESMK_ATTN_IMPL': 'v1'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '1'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '2'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_RESCALE_THRESHOLD': '8', 'ESMK_ATTN_VARIANT': '3'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_VARIANT': '0'},
-    {'ESMK_ATTN_IMPL': 'v5', 'ESMK_ATTN_VARIANT': '2'},
-]
+CONFIGS = [{'ESMK_ATTN_RESCALE_THRESHOLD': t} for t in ('0', '1', '2', '3', '4', '8')] + \
+          [{'ESMK_ATTN_RESCALE_THRESHOLD': '2', 'ESMK_ATTN_POLY': '1'}]
 
 
 def rel(a, b):
