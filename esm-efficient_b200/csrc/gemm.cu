@@ -42,6 +42,15 @@ constexpr int STAGES_PAIR = 6;         // 2-CTA mode: 16 KB A + 16 KB half-W per
 // activity falling with output bytes per FLOP before this change).
 constexpr int STORE_STAGING = 32 * 1024;
 constexpr int BAR_REGION = 1024;
+// RESIDUAL epilogue in pair mode: the residual tile is PREFETCHED by TMA into the warp's staging slot (one 32-row x
+// 64-column box per warp and tile, issued before the accumulator wait) instead of 8 scattered 16-byte loads per
+// thread (32 half-used sectors per instruction; ncu: long_scoreboard 11-40 warps per issue in the epilogue of the
+// N = 1280 GEMMs).  The result is written back into the same slot and leaves through one TMA store.  That needs
+// 4 KB per epilogue warp (64 KB), paid for with one pipeline stage (5 instead of 6).
+constexpr int STAGES_PAIR_RESID = 5;
+constexpr int STORE_STAGING_RESID = 64 * 1024;
+static_assert(STAGES_PAIR_RESID * (BM * BK * 2 + BN * BK) + STORE_STAGING_RESID == 6 * (BM * BK * 2 + BN * BK) + STORE_STAGING,
+              "same smem footprint");
 constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + BAR_REGION + STORE_STAGING + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(STAGES_PAIR * (A_STAGE + B_STAGE / 2) == STAGES * (A_STAGE + B_STAGE), "same smem footprint");
@@ -60,6 +69,7 @@ struct EpiParams {
   int rope_cols;
   int vec_ok;  // 16-byte accesses allowed on C / R / bias (alignment and N % 8 == 0)
   int tma_store;  // tmC is valid: whole 64-column groups leave through shared memory + TMA stores
+  int tma_resid;  // RESIDUAL, pair mode: tmR is valid and tmC has 32 x 64 boxes (residual prefetched by TMA)
 };
 
 // exact-erf GELU:  gelu(x) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2,
@@ -229,10 +239,13 @@ __device__ __forceinline__ void rope64_packed(uint32_t (&w)[32], const uint32_t 
 template <int EPI, int HD, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiParams ep) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int K,
+            EpiParams ep) {
   griddep_launch_dependents();   // the next kernel's launch + prologue may overlap this kernel's tail
   constexpr int EPI_WARPS = epi_warps(EPI);
-  constexpr int NSTAGE = PAIR ? STAGES_PAIR : STAGES;
+  constexpr bool RESID_TMA = PAIR && EPI == ESMK_EPI_RESIDUAL;     // (run-time switch: ep.tma_resid)
+  constexpr int NSTAGE = RESID_TMA ? STAGES_PAIR_RESID : (PAIR ? STAGES_PAIR : STAGES);
+  constexpr int STAGING = RESID_TMA ? STORE_STAGING_RESID : STORE_STAGING;
   constexpr int BSTAGE = PAIR ? B_STAGE / 2 : B_STAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -244,8 +257,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_full = bars + 2 * NSTAGE; // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* r_full = bars + 32;           // [EPI_WARPS] residual tile of the warp has landed (RESID_TMA)
   uint8_t* store_slot = smem + NSTAGE * (A_STAGE + BSTAGE) + BAR_REGION +
-                        (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * (STORE_STAGING / EPI_WARPS) : 0);
+                        (threadIdx.x >= 64 ? ((threadIdx.x >> 5) - 2) * (STAGING / EPI_WARPS) : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -261,7 +275,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (ep.tma_store) tma_prefetch_desc(&tmC);
+    if (ep.tma_store || ep.tma_resid) tma_prefetch_desc(&tmC);
+    if (RESID_TMA && ep.tma_resid) {
+      tma_prefetch_desc(&tmR);
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&r_full[w], 1);
+    }
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);   // pair: the leader arms it with the bytes of BOTH CTAs' loads
       mbar_init(&empty[s], 1);
@@ -346,6 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue, 16 warps: bias / GELU / residual =====================
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int cg = (warp - 2) >> 2;      // which 64-column group of the tile this warp owns
+    [[maybe_unused]] uint32_t r_phase = 0;   // r_full completes once per tile that takes the TMA-residual path
     int it = 0;
     for (int tile = group; tile < num_tiles; tile += n_groups, ++it) {
       const int as = it & 1;
@@ -355,6 +374,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
       const bool full = ep.vec_ok && (n0 + 64 <= N);   // all 64 columns exist and 16-byte accesses are legal
+
+      if constexpr (RESID_TMA) {
+        if (ep.tma_resid && full) {
+          // ---- residual tile by TMA: x + bf(bf(A W^T + b) / s) on a 32-row x 64-column box per warp ----
+          uint64_t* rbar = &r_full[warp - 2];
+          if (lane == 0) {
+            tma_store_wait_read<0>();                  // the previous tile's store out of this slot has been read
+            mbar_arrive_expect_tx(rbar, 32 * 128);
+            tma_load_2d(store_slot, &tmR, rbar, n0, m0 + quad * 32);
+          }
+          const bool has_bias = ep.bias != nullptr;
+          uint32_t bias_w = 0;                         // columns n0 + 2*lane, n0 + 2*lane + 1; handed out by shuffles
+          if (has_bias) bias_w = __ldg(reinterpret_cast<const uint32_t*>(ep.bias + n0) + lane);
+          mbar_wait(&acc_full[as], aphase);
+          tc_fence_after();
+          mbar_wait(rbar, r_phase);
+          r_phase ^= 1;
+          // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7); one row = 128 bytes
+          uint8_t* srow = store_slot + lane * 128;
+          const int sw = lane & 7;
+          // (every lane reads and rewrites only its OWN row of the slot: no cross-lane hazard, chunk by chunk in place)
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + cg * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r0[32];
+            tmem_ld32(t_row + c * 32, r0);
+            tmem_wait_ld();
+            if (c == 1) {   // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+                else mbar_arrive(&acc_empty[as]);
+              }
+            }
+            uint32_t w[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              float lo = __uint_as_float(r0[2 * p]), hi = __uint_as_float(r0[2 * p + 1]);
+              if (has_bias) {
+                const uint32_t b2 = __shfl_sync(0xffffffffu, bias_w, c * 16 + p);
+                lo += bf16_lo(b2);
+                hi += bf16_hi(b2);
+              }
+              w[p] = pack_bf16(lo, hi);                                      // bf(A W^T + b)
+            }
+            if (ep.scale != 1.0f) {                                          // bf(y / s)
+#pragma unroll
+              for (int p = 0; p < 16; ++p)
+                w[p] = pack_bf16(div_scale(bf16_lo(w[p]), ep.scale, ep.inv_scale),
+                                 div_scale(bf16_hi(w[p]), ep.scale, ep.inv_scale));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                    // bf(x + y), packed
+              const uint4 r = *reinterpret_cast<const uint4*>(srow + (((c * 4 + j) ^ sw) << 4));
+              *reinterpret_cast<uint4*>(srow + (((c * 4 + j) ^ sw) << 4)) =
+                  make_uint4(badd2(r.x, w[4 * j]), badd2(r.y, w[4 * j + 1]), badd2(r.z, w[4 * j + 2]), badd2(r.w, w[4 * j + 3]));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, store_slot, n0, m0 + quad * 32);              // rows / columns beyond M, N are clipped
+            tma_store_commit();
+          }
+          continue;
+        }
+      }
 
       // ---- operands fetched BEFORE waiting for the accumulator: their latency hides behind this tile's MMAs
       const bool lane_bias = (EPI != ESMK_EPI_BIAS_GELU) && full && ep.bias != nullptr;
@@ -769,8 +856,8 @@ bool use_pair_mode() {
 }
 
 template <int EPI, int HD, bool PAIR>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                const EpiParams& ep, cudaStream_t st) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR, int M,
+                int N, int K, const EpiParams& ep, cudaStream_t st) {
   auto kern = gemm_kernel<EPI, HD, PAIR>;
   static std::atomic<uint64_t> configured{0};   // per device: a process may use several GPUs
   if (needs_config(configured)) {
@@ -803,7 +890,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   cfg.blockDim = dim3(gemm_threads(EPI));
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, ep));
+  ESMK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, M, N, K, ep));
   count_launch();
   return 0;
 }
@@ -838,38 +925,48 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   // output tensor map of the TMA-store epilogue: 32-row boxes of one warp's column chunk
   CUtensorMap tmC = tmA;
   static const bool tma_store_enabled = [] { const char* e = getenv("ESMK_GEMM_TMA_STORE"); return e == nullptr || e[0] != '0'; }();
+  CUtensorMap tmR = tmA;
   ep.tma_store = 0;
+  ep.tma_resid = 0;
+  static const bool tma_resid_enabled = [] { const char* e = getenv("ESMK_GEMM_TMA_RESID"); return e == nullptr || e[0] != '0'; }();
   if (ep.vec_ok && tma_store_enabled) {
-    const bool wide = a.epilogue == ESMK_EPI_QKV_ROPE;          // 8-warp epilogue, 64-column groups
-    ESMK_TRY(make_tmap_2d(&tmC, a.C, a.M, n_out, a.ldc, 32, wide ? 64 : 32, wide ? 128 : 64));
-    ep.tma_store = 1;
+    if (pair && a.epilogue == ESMK_EPI_RESIDUAL && tma_resid_enabled && a.R != nullptr) {
+      // residual prefetched by TMA, result written over it in the warp's slot: 32-row x 64-column boxes both ways
+      ESMK_TRY(make_tmap_2d(&tmC, a.C, a.M, n_out, a.ldc, 32, 64, 128));
+      ESMK_TRY(make_tmap_2d(&tmR, a.R, a.M, n_out, a.ldr, 32, 64, 128));
+      ep.tma_resid = 1;      // (groups at a ragged right edge take the element-wise path: tma_store stays 0)
+    } else {
+      const bool wide = a.epilogue == ESMK_EPI_QKV_ROPE;          // 8-warp epilogue, 64-column groups
+      ESMK_TRY(make_tmap_2d(&tmC, a.C, a.M, n_out, a.ldc, 32, wide ? 64 : 32, wide ? 128 : 64));
+      ep.tma_store = 1;
+    }
   }
   switch (a.epilogue) {
     case ESMK_EPI_BIAS:
-      return pair ? launch_impl<ESMK_EPI_BIAS, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_BIAS, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS, 64, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS, 64, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_BIAS_GELU:
-      return pair ? launch_impl<ESMK_EPI_BIAS_GELU, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_BIAS_GELU, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_BIAS_GELU, 64, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_BIAS_GELU, 64, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_RESIDUAL:
       ESMK_REQUIRE(a.R != nullptr && a.residue_scaling != 0.f, "residual epilogue needs R and a non-zero scale");
       ep.vec_ok = ep.vec_ok && (a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
-      return pair ? launch_impl<ESMK_EPI_RESIDUAL, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_RESIDUAL, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_RESIDUAL, 64, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_RESIDUAL, 64, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_SWIGLU:
       ESMK_REQUIRE(a.N % 64 == 0, "SwiGLU epilogue needs N (= 2F) to be a multiple of 64");
       ESMK_REQUIRE(a.bias == nullptr, "SwiGLU epilogue has no bias (ESMC linears are bias-free)");
-      return pair ? launch_impl<ESMK_EPI_SWIGLU, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_SWIGLU, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      return pair ? launch_impl<ESMK_EPI_SWIGLU, 64, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_SWIGLU, 64, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
     case ESMK_EPI_QKV_ROPE:
       ESMK_REQUIRE(a.rope_cos && a.rope_sin && a.pos, "QKV_ROPE epilogue needs cos/sin tables and positions");
       ESMK_REQUIRE(a.rope_cols % 64 == 0 && a.rope_cols <= a.N, "rope_cols must be a multiple of 64 and <= N");
-      if (a.head_dim == 64) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 64, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 64, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 32) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 32, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 32, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
-      if (a.head_dim == 16) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 16, true>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st)
-                  : launch_impl<ESMK_EPI_QKV_ROPE, 16, false>(tmA, tmB, tmC, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 64) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 64, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 64, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 32) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 32, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 32, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
+      if (a.head_dim == 16) return pair ? launch_impl<ESMK_EPI_QKV_ROPE, 16, true>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st)
+                  : launch_impl<ESMK_EPI_QKV_ROPE, 16, false>(tmA, tmB, tmC, tmR, a.M, a.N, a.K, ep, st);
       return fail("esmk_gemm", "fused QKV_ROPE supports head_dim 16/32/64; use ESMK_EPI_BIAS + esmk_qk_norm_rope");
     default:
       return fail("esmk_gemm", "unknown epilogue");
