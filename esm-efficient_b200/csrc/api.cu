@@ -48,6 +48,14 @@ int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D
                const uint8_t* zero_rows, esmk_stream_t s) {
   GUARD(esmk::embed(tokens, table, out, T, D, vocab, zero_token, zero_rows, ST(s)));
 }
+int esmk_unpad_tokens(const int64_t* tokens2d, int B, int S, int pad_token, int64_t* packed, int64_t* indices,
+                      int32_t* cu_lens, int32_t* lens_scratch, int32_t* meta, esmk_stream_t s) {
+  GUARD(esmk::unpad_tokens(tokens2d, B, S, pad_token, packed, indices, cu_lens, lens_scratch, meta, ST(s)));
+}
+int esmk_pad_rows(const void* x, int ldx, const int64_t* indices, int T, void* out, int rows, int D,
+                  int32_t* inverse_scratch, esmk_stream_t s) {
+  GUARD(esmk::pad_rows(x, ldx, indices, T, out, rows, D, inverse_scratch, ST(s)));
+}
 int esmk_add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset, esmk_stream_t s) {
   GUARD(esmk::add_positions(x, table, pos, T, D, rows, offset, ST(s)));
 }

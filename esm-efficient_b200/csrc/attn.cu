@@ -17,7 +17,7 @@
 //   - O accumulates in TMEM and is rescaled whenever a row maximum outgrows the reference its P values were scaled
 //     with by more than `rescale_threshold` (log2 units).  Default 0 = the exact running maximum of
 //     FlashAttention-2, the kernel the reference calls: the row's largest P is exactly 1.0 (no rounding error on the
-//     dominant term), which is what round 1's lazy 2^8 threshold gave up (1.14x the oracle's noise; now 0.98x);
+//     dominant term), which is what round 1's lazy 2^8 threshold gave up (1.14x the noise of the reference kernel's bf16 restatement; now 0.98x);
 //   - the last key block of a sequence is trimmed: the S MMA runs with N = valid keys rounded up to 16, the
 //     P.V MMA with as many 16-key steps, and the softmax warps skip 32-column chunks without valid keys;
 //     warps whose 32 query rows lie beyond the sequence end only keep the barrier protocol.
@@ -689,7 +689,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     }
     // log2 units by which a row maximum may outgrow the reference its P values are scaled with before O is rescaled.
     // 0 = the exact running maximum of FlashAttention-2.  Measured (tools/attn_ab.py: rms-relative error against the
-    // exact fp64 attention on the same bf16 inputs -- flash-attn 2.8.3 1.886e-3, oracle 1.931e-3 -- and time on the
+    // exact fp64 attention on the same bf16 inputs -- flash-attn 2.8.3 1.886e-3, its CPU bf16 restatement 1.931e-3 -- and time on the
     // config-2 batch):  0: 1.887e-3 0.352 ms | 1: 1.943e-3 0.349 | 2: 1.996e-3 0.340 | 3: 2.053e-3 0.333 |
     //                   4: 2.110e-3 0.332 | 8: 2.209e-3 0.332 (round 1).  Parity first: the default is 0.
     static const float threshold = [] {

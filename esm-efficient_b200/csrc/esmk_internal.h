@@ -18,6 +18,10 @@ int batch_meta(const int32_t* cu_lens, int B, int T, int32_t* pos, int32_t* tile
 int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st);
 int embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
           const uint8_t* zero_rows, cudaStream_t st);
+int unpad_tokens(const int64_t* tokens2d, int B, int S, int pad_token, int64_t* packed, int64_t* indices,
+                 int32_t* cu_lens, int32_t* lens_scratch, int32_t* meta, cudaStream_t st);
+int pad_rows(const void* x, int ldx, const int64_t* indices, int T, void* out, int rows, int D, int32_t* inverse_scratch,
+             cudaStream_t st);
 int add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset, cudaStream_t st);
 int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
               cudaStream_t st);

@@ -1,6 +1,8 @@
 // Whole-model driver: the packed forward pass as a fixed sequence of esmk kernels
 // on one stream (no host synchronisation, CUDA-graph capturable).  Replaces the
 // Python layer loop of esme/esm.py:229-252 and the head of esme/head.py:25-27.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -11,6 +13,22 @@ struct esmk_model {
   esmk_config cfg;
   esmk_weights w;
   std::vector<esmk_layer_weights> layers;
+  // Quantised weights only: a side stream + events that expand weight n+2 into the second scratch buffer while the
+  // GEMM of weight n runs (the expansion kernel needs no shared memory and co-resides with the persistent GEMM
+  // CTAs), created lazily on the device of the first forward.  One forward in flight per quantised model handle.
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  int aux_device = -1;
+  ~esmk_model() {
+    if (aux_device < 0) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(aux_device);
+    for (cudaEvent_t e : {ev_fork, ev_ready[0], ev_ready[1], ev_free[0], ev_free[1]})
+      if (e) cudaEventDestroy(e);
+    if (aux) cudaStreamDestroy(aux);
+    cudaSetDevice(cur);
+  }
 };
 
 namespace esmk {
@@ -72,7 +90,7 @@ struct Workspace {
 };
 
 struct Buffers {
-  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb, *wq, *qkvp, *ap;
+  __nv_bfloat16 *x, *h, *qkv, *a, *u, *cosb, *sinb, *wq, *wq2, *qkvp, *ap;
   int32_t *pos, *tile_info;
   size_t bytes;
 };
@@ -104,7 +122,8 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len, size_t 
   b.sinb = w.take<__nv_bfloat16>((size_t)max_len * hd);
   b.pos = w.take<int32_t>((size_t)T);
   b.tile_info = w.take<int32_t>((size_t)4 * tile_capacity(T, B));
-  b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;
+  b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;     // two scratch weights: one being read by a GEMM,
+  b.wq2 = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;    // one being expanded for the GEMM after next
   // small head dims: heads zero-padded to 64 columns for the tcgen05 attention kernel (see pad_heads)
   const bool pad = hd < 64;
   b.qkvp = pad ? w.take<__nv_bfloat16>((size_t)T * 3 * c.attention_heads * 64) : nullptr;
@@ -121,15 +140,68 @@ int linear(const void* A, int lda, const void* W, const void* bias, void* C, int
   return gemm(g, st);
 }
 
-// the bf16 weight a GEMM should read: the caller's, or the scratch freshly expanded from quantised storage
-int weight_of(const void* w, const esmk_qweight& q, int N, int K, __nv_bfloat16* scratch, cudaStream_t st, const void** out) {
-  if (q.data == nullptr) {
-    *out = w;
+// ---------------------------------------------------------------------------
+// Quantised weights -> bf16 scratch, two GEMMs ahead of their consumer on a side stream.
+// ---------------------------------------------------------------------------
+struct QItem { const esmk_qweight* q; int N, K; };
+
+struct QPipe {
+  esmk_model* m;
+  std::vector<QItem> items;      // the quantised weights of one forward, in the order their GEMMs run
+  __nv_bfloat16* scratch[2];
+  cudaStream_t main;
+  bool overlap;
+  size_t next = 0;               // next item to hand to a GEMM
+
+  int expand(size_t n, cudaStream_t st) {
+    const QItem& it = items[n];
+    return dequantize(it.q->data, it.q->scale, it.N, it.K, it.q->bits, scratch[n & 1], st);
+  }
+  int start() {
+    if (items.empty()) return 0;
+    if (!overlap) return 0;
+    ESMK_CUDA(cudaEventRecord(m->ev_fork, main));                 // the side stream starts behind everything queued so far
+    ESMK_CUDA(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+    for (size_t n = 0; n < 2 && n < items.size(); ++n) {
+      ESMK_TRY(expand(n, m->aux));
+      ESMK_CUDA(cudaEventRecord(m->ev_ready[n & 1], m->aux));
+    }
     return 0;
   }
-  Span span(ESMK_PROF_DEQUANT, st);
-  *out = scratch;
-  return dequantize(q.data, q.scale, N, K, q.bits, scratch, st);
+  // the bf16 weight the next GEMM should read (call in GEMM order; `w` = the caller's bf16 weight when not quantised)
+  int weight(const void* w, const esmk_qweight& q, const void** out) {
+    if (q.data == nullptr) { *out = w; return 0; }
+    const size_t n = next++;
+    *out = scratch[n & 1];
+    if (!overlap) {
+      Span span(ESMK_PROF_DEQUANT, main);
+      return expand(n, main);
+    }
+    ESMK_CUDA(cudaStreamWaitEvent(main, m->ev_ready[n & 1], 0));
+    return 0;
+  }
+  // after the GEMM that read item n has been enqueued: its scratch may be refilled with item n + 2
+  int consumed() {
+    if (!overlap || next == 0) return 0;
+    const size_t n = next - 1;
+    if (n + 2 >= items.size()) return 0;
+    ESMK_CUDA(cudaEventRecord(m->ev_free[n & 1], main));
+    ESMK_CUDA(cudaStreamWaitEvent(m->aux, m->ev_free[n & 1], 0));
+    ESMK_TRY(expand(n + 2, m->aux));
+    ESMK_CUDA(cudaEventRecord(m->ev_ready[n & 1], m->aux));
+    return 0;
+  }
+};
+
+int ensure_aux(esmk_model* m) {
+  const int dev = current_device();
+  if (m->aux_device == dev) return 0;
+  ESMK_REQUIRE(m->aux_device < 0, "a quantised model handle is bound to the device of its first forward");
+  ESMK_CUDA(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&m->ev_fork, &m->ev_ready[0], &m->ev_ready[1], &m->ev_free[0], &m->ev_free[1]})
+    ESMK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  m->aux_device = dev;
+  return 0;
 }
 
 int head_and_output(const esmk_model* m, const __nv_bfloat16* z, int T, __nv_bfloat16* t0, __nv_bfloat16* t1,
@@ -224,6 +296,22 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
   const float s = c.residue_scaling;
   const bool fused_rope = (c.family == 0) && !c.no_rotary && (hd == 16 || hd == 32 || hd == 64) && ((2 * D) % 64 == 0);
 
+  QPipe qp{m, {}, {b.wq, b.wq2}, st, false};
+  {
+    const int F1 = c.family == 0 ? F : 2 * F;
+    for (const esmk_layer_weights& l : m->layers) {
+      if (l.q_wqkv.data) qp.items.push_back({&l.q_wqkv, 3 * D, D});
+      if (l.q_wo.data) qp.items.push_back({&l.q_wo, D, D});
+      if (l.q_w1.data) qp.items.push_back({&l.q_w1, F1, D});
+      if (l.q_w2.data) qp.items.push_back({&l.q_w2, D, F});
+    }
+    static const bool overlap_enabled = [] { const char* e = getenv("ESMK_QUANT_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+    if (!qp.items.empty() && overlap_enabled) {
+      ESMK_TRY(ensure_aux(m));
+      qp.overlap = true;
+    }
+    ESMK_TRY(qp.start());
+  }
   PROF(ESMK_PROF_MISC, batch_meta(cu_lens, B, T, b.pos, b.tile_info, st));
   PROF(ESMK_PROF_MISC, rope_tables(b.cosb, b.sinb, max_len, hd, st));
   // esme/esm.py:188-189: ESM2 zeroes <mask>(32) rows; ESMC (esm.py:876) does not
@@ -239,15 +327,17 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
     // ---- attention block: x = x + out(attn(rope(qkv(LN(x))))) / s   (esme/attention.py:126-139, 253-254)
     PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.attn_norm_w, l.attn_norm_b, b.h, D, T, D, 1e-5f, st));
     const void *wqkv, *wo, *w1, *w2;
-    ESMK_TRY(weight_of(l.wqkv, l.q_wqkv, 3 * D, D, b.wq, st, &wqkv));
+    ESMK_TRY(qp.weight(l.wqkv, l.q_wqkv, &wqkv));
     if (fused_rope) {
       esmk_gemm_args g{};
       g.A = b.h; g.lda = D; g.W = wqkv; g.bias = l.bqkv; g.C = b.qkv; g.ldc = 3 * D;
       g.M = T; g.N = 3 * D; g.K = D; g.epilogue = ESMK_EPI_QKV_ROPE;
       g.rope_cos = b.cosb; g.rope_sin = b.sinb; g.pos = b.pos; g.head_dim = hd; g.rope_cols = 2 * D;
       PROF(ESMK_PROF_GEMM_QKV, gemm(g, st));
+      if (l.q_wqkv.data) ESMK_TRY(qp.consumed());
     } else {
       PROF(ESMK_PROF_GEMM_QKV, linear(b.h, D, wqkv, l.bqkv, b.qkv, 3 * D, T, 3 * D, D, ESMK_EPI_BIAS, st));
+      if (l.q_wqkv.data) ESMK_TRY(qp.consumed());
       if (!c.no_rotary || l.qln_w != nullptr)
         PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, c.no_rotary ? nullptr : b.cosb,
                                           c.no_rotary ? nullptr : b.sinb, b.pos, st));
@@ -262,18 +352,21 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
       PROF(ESMK_PROF_ATTENTION,
            attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));
     }
-    ESMK_TRY(weight_of(l.wo, l.q_wo, D, D, b.wq, st, &wo));
+    ESMK_TRY(qp.weight(l.wo, l.q_wo, &wo));
     PROF(ESMK_PROF_GEMM_OUT, linear(b.a, D, wo, l.bo, b.x, D, T, D, D, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    if (l.q_wo.data) ESMK_TRY(qp.consumed());
     // ---- FFN block: x = x + final(x) / s   (esme/attention.py:217-236, 255)
     PROF(ESMK_PROF_LAYERNORM, layernorm(b.x, D, l.ffn_norm_w, l.ffn_norm_b, b.h, D, T, D, 1e-5f, st));
-    ESMK_TRY(weight_of(l.w1, l.q_w1, c.family == 0 ? F : 2 * F, D, b.wq, st, &w1));
+    ESMK_TRY(qp.weight(l.w1, l.q_w1, &w1));
     if (c.family == 0) {
       PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, w1, l.b1, b.u, F, T, F, D, ESMK_EPI_BIAS_GELU, st));
     } else {
       PROF(ESMK_PROF_GEMM_FFN_UP, linear(b.h, D, w1, nullptr, b.u, F, T, 2 * F, D, ESMK_EPI_SWIGLU, st));
     }
-    ESMK_TRY(weight_of(l.w2, l.q_w2, D, F, b.wq, st, &w2));
+    if (l.q_w1.data) ESMK_TRY(qp.consumed());
+    ESMK_TRY(qp.weight(l.w2, l.q_w2, &w2));
     PROF(ESMK_PROF_GEMM_FFN_DOWN, linear(b.u, F, w2, l.b2, b.x, D, T, D, F, ESMK_EPI_RESIDUAL, st, b.x, D, s));
+    if (l.q_w2.data) ESMK_TRY(qp.consumed());
     if (layer_taps != nullptr && layer_taps[i] != nullptr)
       ESMK_CUDA(cudaMemcpyAsync(layer_taps[i], b.x, (size_t)T * D * 2, cudaMemcpyDeviceToDevice, st));
   }

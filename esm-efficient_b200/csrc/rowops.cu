@@ -138,6 +138,131 @@ int rope_tables(void* cosb, void* sinb, int max_len, int hd, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// Padded [B,S] token grid -> packed batch (flash_attn.bert_padding.unpad_input as the reference calls it at
+// esme/esm.py:238) and back (pad_input, esme/esm.py:255-261).
+//   unpad_count_kernel : one block per row: number of kept (non-pad) tokens
+//   unpad_scan_kernel  : one block: cu_lens = exclusive scan of the row lengths; meta = {T, max_len}
+//   unpad_fill_kernel  : one block per row: packed tokens and their flat grid indices b*S + s, in row order
+// Each thread owns a contiguous chunk of the row; a block scan of the chunk counts gives its output offset.
+// ---------------------------------------------------------------------------
+constexpr int kPadThreads = 256;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem, int* total) {
+  // smem: kPadThreads ints.  Hillis-Steele over the block (row lengths are a few thousand at most).
+  const int t = threadIdx.x;
+  smem[t] = v;
+  __syncthreads();
+  for (int off = 1; off < kPadThreads; off <<= 1) {
+    const int add = t >= off ? smem[t - off] : 0;
+    __syncthreads();
+    smem[t] += add;
+    __syncthreads();
+  }
+  const int incl = smem[t];
+  if (total != nullptr) *total = smem[kPadThreads - 1];
+  __syncthreads();
+  return incl - v;
+}
+
+__global__ void __launch_bounds__(kPadThreads)
+unpad_count_kernel(const int64_t* __restrict__ tokens, int S, long long pad, int32_t* __restrict__ lens) {
+  __shared__ int sm[kPadThreads];
+  const int64_t* row = tokens + (size_t)blockIdx.x * S;
+  const int per = (S + kPadThreads - 1) / kPadThreads;
+  const int s0 = threadIdx.x * per, s1 = min(S, s0 + per);
+  int n = 0;
+  for (int i = s0; i < s1; ++i) n += row[i] != pad;
+  int total;
+  block_exclusive_scan(n, sm, &total);
+  if (threadIdx.x == 0) lens[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kPadThreads)
+unpad_scan_kernel(const int32_t* __restrict__ lens, int B, int32_t* __restrict__ cu_lens, int32_t* __restrict__ meta) {
+  __shared__ int sm[kPadThreads];
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  const int per = (B + kPadThreads - 1) / kPadThreads;
+  const int b0 = threadIdx.x * per, b1 = min(B, b0 + per);
+  int n = 0, mx = 0;
+  for (int i = b0; i < b1; ++i) { n += lens[i]; mx = max(mx, lens[i]); }
+  int total;
+  int off = block_exclusive_scan(n, sm, &total);
+  atomicMax(&s_max, mx);
+  for (int i = b0; i < b1; ++i) { cu_lens[i] = off; off += lens[i]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cu_lens[B] = total;
+    meta[0] = total;
+    meta[1] = s_max;
+  }
+}
+
+__global__ void __launch_bounds__(kPadThreads)
+unpad_fill_kernel(const int64_t* __restrict__ tokens, int S, long long pad, const int32_t* __restrict__ cu_lens,
+                  int64_t* __restrict__ packed, int64_t* __restrict__ indices) {
+  __shared__ int sm[kPadThreads];
+  const int64_t* row = tokens + (size_t)blockIdx.x * S;
+  const int per = (S + kPadThreads - 1) / kPadThreads;
+  const int s0 = threadIdx.x * per, s1 = min(S, s0 + per);
+  int n = 0;
+  for (int i = s0; i < s1; ++i) n += row[i] != pad;
+  int o = cu_lens[blockIdx.x] + block_exclusive_scan(n, sm, nullptr);
+  for (int i = s0; i < s1; ++i) {
+    const long long t = row[i];
+    if (t != pad) {
+      packed[o] = t;
+      indices[o] = (long long)blockIdx.x * S + i;
+      ++o;
+    }
+  }
+}
+
+int unpad_tokens(const int64_t* tokens2d, int B, int S, int pad_token, int64_t* packed, int64_t* indices,
+                 int32_t* cu_lens, int32_t* lens_scratch, int32_t* meta, cudaStream_t st) {
+  ESMK_REQUIRE(tokens2d && packed && indices && cu_lens && lens_scratch && meta, "null argument");
+  ESMK_REQUIRE(B >= 1 && S >= 1, "empty token grid");
+  unpad_count_kernel<<<B, kPadThreads, 0, st>>>(tokens2d, S, pad_token, lens_scratch);
+  unpad_scan_kernel<<<1, kPadThreads, 0, st>>>(lens_scratch, B, cu_lens, meta);
+  unpad_fill_kernel<<<B, kPadThreads, 0, st>>>(tokens2d, S, pad_token, cu_lens, packed, indices);
+  count_launch(3);
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[rows, D] = 0 except out[indices[t]] = x[t]   (pad_input): one warp per OUTPUT row, so the zero fill and the
+// scatter are one pass; inverse[r] = packed row of grid cell r or -1 is built by pad_inverse_kernel first.
+__global__ void pad_inverse_kernel(const int64_t* __restrict__ indices, int T, int32_t* __restrict__ inverse) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) inverse[indices[t]] = t;
+}
+__global__ void pad_rows_kernel(const uint4* __restrict__ x, int ldx8, const int32_t* __restrict__ inverse,
+                                uint4* __restrict__ out, int rows, int D8) {
+  const int r = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int t = inverse[r];
+  uint4* dst = out + (size_t)r * D8;
+  const uint4* src = x + (size_t)max(t, 0) * ldx8;
+  for (int c = lane; c < D8; c += 32) dst[c] = t >= 0 ? src[c] : make_uint4(0, 0, 0, 0);
+}
+
+int pad_rows(const void* x, int ldx, const int64_t* indices, int T, void* out, int rows, int D, int32_t* inverse_scratch,
+             cudaStream_t st) {
+  ESMK_REQUIRE(out && inverse_scratch && rows >= 0 && T >= 0 && T <= rows, "pad_rows: bad arguments");
+  ESMK_REQUIRE(D % 8 == 0 && ldx % 8 == 0, "pad_rows needs D and the pitch to be multiples of 8");
+  if (rows == 0) return 0;
+  ESMK_CUDA(cudaMemsetAsync(inverse_scratch, 0xff, (size_t)rows * sizeof(int32_t), st));
+  if (T > 0) pad_inverse_kernel<<<(T + 255) / 256, 256, 0, st>>>(indices, T, inverse_scratch);
+  pad_rows_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+      (const uint4*)x, ldx / 8, inverse_scratch, (uint4*)out, rows, D / 8);
+  count_launch(T > 0 ? 2 : 1);
+  ESMK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // embedding gather
 // ---------------------------------------------------------------------------
 __global__ void embed_kernel(const int64_t* __restrict__ tokens, const uint4* __restrict__ table,

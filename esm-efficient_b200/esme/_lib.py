@@ -82,6 +82,8 @@ SIGNATURES = {
     'esmk_batch_meta': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_rope_tables': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'esmk_embed': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'esmk_unpad_tokens': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'esmk_pad_rows': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'esmk_add_positions': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'esmk_layernorm': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     'esmk_qk_norm_rope': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

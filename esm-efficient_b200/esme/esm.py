@@ -267,13 +267,10 @@ class ESM2(nn.Module):
 
     def _unpad(self, tokens2d):
         """Packed view of a padded batch (the job of flash_attn.bert_padding.unpad_input
-        at esme/esm.py:238): -> tokens[T], indices[T] into the [B,S] grid, cu_lens int32[B+1], max_len."""
-        keep = tokens2d.ne(self._alphabet.padding_idx)
-        lens = keep.sum(dim=1, dtype=torch.int32)
-        cu_lens = torch.zeros(tokens2d.shape[0] + 1, dtype=torch.int32, device=tokens2d.device)
-        cu_lens[1:] = torch.cumsum(lens, 0)
-        indices = torch.nonzero(keep.flatten(), as_tuple=False).flatten()
-        return tokens2d.flatten()[indices].contiguous(), indices, cu_lens, int(lens.max().item())
+        at esme/esm.py:238): -> tokens[T], indices[T] into the [B,S] grid, cu_lens int32[B+1], max_len.
+        Three small libesmk kernels and one 8-byte read-back (esmk_unpad_tokens)."""
+        ops._need_cuda(tokens2d)
+        return ops.unpad_tokens(tokens2d, self._alphabet.padding_idx)
 
     def _check_layers(self, layers):
         layers = layers or list()
@@ -333,9 +330,8 @@ class ESM2(nn.Module):
 
     @staticmethod
     def _pad(x, indices, rows):
-        full = torch.zeros(rows, x.shape[-1], dtype=x.dtype, device=x.device)
-        full[indices] = x
-        return full
+        """pad_input (esme/esm.py:255-261): zero rows for the padding cells (esmk_pad_rows)."""
+        return ops.pad_rows(x.contiguous(), indices, rows)
 
     def forward_representation(self, tokens, pad_args=None, pad_output=False, pad_indices=None,
                                lora_names=None, layers=None):

@@ -274,3 +274,36 @@ def add_positions_(x: torch.Tensor, table: torch.Tensor, pos: torch.Tensor, offs
     L.check(L.lib.esmk_add_positions(x.data_ptr(), table.data_ptr(), pos.data_ptr(), x.shape[0], x.shape[1],
                                      table.shape[0], offset, _stream()), 'esmk_add_positions')
     return x
+
+
+@_on_tensor_device
+def unpad_tokens(tokens2d: torch.Tensor, pad_token: int):
+    """[B,S] int64 token grid -> (packed tokens int64[T], flat grid indices int64[T], cu_lens int32[B+1], max_len):
+    the job of flash_attn.bert_padding.unpad_input at esme/esm.py:238, on the device; ONE 8-byte read-back of
+    {T, max_len} is the entry's only synchronisation (the reference's path has three)."""
+    _need_cuda(tokens2d)
+    assert tokens2d.ndim == 2 and tokens2d.dtype == torch.int64
+    t2 = tokens2d.contiguous()
+    B, S = t2.shape
+    dev = t2.device
+    packed = torch.empty(B * S, dtype=torch.int64, device=dev)
+    indices = torch.empty(B * S, dtype=torch.int64, device=dev)
+    cu_lens = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    lens = torch.empty(B, dtype=torch.int32, device=dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)
+    L.check(L.lib.esmk_unpad_tokens(t2.data_ptr(), B, S, int(pad_token), packed.data_ptr(), indices.data_ptr(),
+                                    cu_lens.data_ptr(), lens.data_ptr(), meta.data_ptr(), _stream()), 'esmk_unpad_tokens')
+    T, max_len = (int(v) for v in meta.tolist())
+    return packed[:T], indices[:T], cu_lens, max_len
+
+
+@_on_tensor_device
+def pad_rows(x: torch.Tensor, indices: torch.Tensor, rows: int) -> torch.Tensor:
+    """[T,D] packed rows -> [rows, D] with x[t] at row indices[t] and zeros elsewhere (pad_input, esme/esm.py:255-261)."""
+    _need_cuda(x, indices)
+    assert x.dtype == bf16 and x.ndim == 2 and x.stride(1) == 1 and indices.dtype == torch.int64
+    out = torch.empty(rows, x.shape[1], dtype=bf16, device=x.device)
+    inverse = torch.empty(max(rows, 1), dtype=torch.int32, device=x.device)
+    L.check(L.lib.esmk_pad_rows(x.data_ptr(), x.stride(0) if x.shape[0] > 1 else x.shape[1], indices.contiguous().data_ptr(),
+                                x.shape[0], out.data_ptr(), rows, x.shape[1], inverse.data_ptr(), _stream()), 'esmk_pad_rows')
+    return out

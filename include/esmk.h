@@ -70,6 +70,18 @@ ESMK_API int esmk_rope_tables(void* cos, void* sin, int max_len, int head_dim, e
 ESMK_API int esmk_embed(const int64_t* tokens, const void* table, void* out, int T, int D, int vocab, int zero_token,
                const uint8_t* zero_rows, esmk_stream_t stream);
 
+/* Padded token grid <-> packed batch: the jobs of flash_attn.bert_padding.unpad_input / pad_input as the reference
+ * calls them for 2-D token input (esme/esm.py:235-239, 254-261).
+ *   esmk_unpad_tokens: tokens2d int64[B,S]; every token != pad_token is kept, in row-major order:
+ *       packed  int64[B*S] (first T valid)       indices int64[B*S] (flat grid index b*S + s of each packed token)
+ *       cu_lens int32[B+1]                        lens_scratch int32[B]
+ *       meta    int32[2] = {T, max_len} (device; the caller reads it back once -- the only synchronisation of the entry)
+ *   esmk_pad_rows: out[rows, D] (dense) = 0 except out[indices[t]] = x[t] for t < T; inverse_scratch int32[rows]. */
+ESMK_API int esmk_unpad_tokens(const int64_t* tokens2d, int B, int S, int pad_token, int64_t* packed, int64_t* indices,
+                               int32_t* cu_lens, int32_t* lens_scratch, int32_t* meta, esmk_stream_t stream);
+ESMK_API int esmk_pad_rows(const void* x, int ldx, const int64_t* indices, int T, void* out, int rows, int D,
+                           int32_t* inverse_scratch, esmk_stream_t stream);
+
 /* ESM-1b / ESM-1v learned positional embedding, esme/esm.py:634-646 + esme/embedding.py:36-92, in place:
  * x[t] = bf(x[t] + table[pos[t] + offset]); pos from esmk_batch_meta, offset = padding_idx + 1 = 2, table bf16 [rows, D]. */
 ESMK_API int esmk_add_positions(void* x, const void* table, const int32_t* pos, int T, int D, int rows, int offset,

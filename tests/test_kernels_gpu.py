@@ -148,3 +148,30 @@ def test_attention_pool_heads_match_reference():
         y = head(embed, (cu, max_len))
         assert y.shape == g[key].shape
         assert (y.float().cpu() - g[key]).abs().max() <= 0.02 * g[key].abs().max() + 0.02
+
+
+def test_unpad_and_pad_kernels_match_torch():
+    """esmk_unpad_tokens / esmk_pad_rows (the jobs of flash_attn.bert_padding.unpad_input / pad_input at
+    esme/esm.py:238, 255-261) against plain torch indexing, incl. interior pads, an all-pad row and S > 256."""
+    import torch
+    from esme import ops
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(3)
+    for B, S in ((1, 1), (3, 70), (17, 300), (5, 1031)):
+        tok = torch.randint(4, 24, (B, S), generator=g)
+        keep = torch.rand(B, S, generator=g) > 0.3
+        if B > 2:
+            keep[1] = False                                   # a row of padding only
+            keep[2, S // 2:] = False                          # right-padded row (the usual case)
+        tok = torch.where(keep, tok, torch.ones_like(tok))    # 1 = <pad>
+        packed, idx, cu, max_len = ops.unpad_tokens(tok.to(dev), 1)
+        want_idx = torch.nonzero(keep.flatten()).flatten()
+        lens = keep.sum(1)
+        assert torch.equal(idx.cpu(), want_idx) and torch.equal(packed.cpu(), tok.flatten()[want_idx])
+        assert torch.equal(cu.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]))
+        assert max_len == int(lens.max()) and cu.dtype == torch.int32
+        x = torch.randn(int(lens.sum()), 64, generator=g).bfloat16()
+        full = ops.pad_rows(x.to(dev), idx, B * S).cpu()
+        want = torch.zeros(B * S, 64, dtype=torch.bfloat16)
+        want[want_idx] = x
+        assert torch.equal(full, want)
