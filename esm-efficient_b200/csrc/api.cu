@@ -6,6 +6,7 @@
 #include "esmk_internal.h"
 
 struct esmk_model;
+struct esmk_comm;
 
 namespace esmk {
 static std::atomic<uint64_t> g_launches{0};
@@ -94,6 +95,15 @@ int esmk_quantize(const void* W, int N, int K, int bits, void* data, float* scal
 }
 int esmk_dequantize(const void* data, const float* scale, int N, int K, int bits, void* W, esmk_stream_t s) {
   GUARD(esmk::dequantize(data, scale, N, K, bits, W, ST(s)));
+}
+int esmk_comm_unique_id(void* id128) { GUARD(esmk::comm_unique_id(id128)); }
+int esmk_comm_create(esmk_comm_t** out, int world_size, int rank, const void* id128) {
+  GUARD(esmk::comm_create(out, world_size, rank, id128));
+}
+void esmk_comm_destroy(esmk_comm_t* comm) { esmk::comm_destroy(comm); }
+int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_max, int V, const int64_t* perm, int T,
+                          void* gathered, void* out, esmk_stream_t s) {
+  GUARD(esmk::allgather_logits(comm, local, t_max, V, perm, T, gathered, out, ST(s)));
 }
 void esmk_profile_enable(int on) { esmk::profile_enable(on); }
 int esmk_profile_read(float* ms, int* launches, int n_categories) {

@@ -45,6 +45,12 @@ int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, cu
 int attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void* out, const int32_t* cu_lens, int B,
               int C, int H, int hd, cudaStream_t st);
 
+int comm_unique_id(void* id128);
+int comm_create(esmk_comm** out, int world, int rank, const void* id128);
+void comm_destroy(esmk_comm* c);
+int allgather_logits(esmk_comm* c, const void* local, int t_max, int V, const int64_t* perm, int T, void* gathered,
+                     void* out, cudaStream_t st);
+
 void profile_enable(int on);
 int profile_read(float* ms, int* launches, int n_categories);
 

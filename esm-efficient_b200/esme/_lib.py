@@ -103,6 +103,10 @@ SIGNATURES = {
     'esmk_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'esmk_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                              c_int, c_void_p, c_void_p, c_void_p]),
+    'esmk_comm_unique_id': (c_int, [c_void_p]),
+    'esmk_comm_create': (c_int, [C.POINTER(c_void_p), c_int, c_int, c_void_p]),
+    'esmk_comm_destroy': (None, [c_void_p]),
+    'esmk_allgather_logits': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_profile_enable': (None, [c_int]),
     'esmk_profile_read': (c_int, [C.POINTER(c_float), C.POINTER(c_int), c_int]),
     'esmk_lm_head': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),

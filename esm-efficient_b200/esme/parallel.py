@@ -7,10 +7,49 @@ with replicated weights, and ONE collective -- an all-gather of the per-rank
 logits -- restores the original token order on every rank.  No collective is
 needed inside the forward.
 """
-from typing import Callable, List, Sequence, Tuple
+import ctypes as C
+import os
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+class EsmkComm:
+    """NCCL communicator owned by libesmk (esmk_comm_t): the collective of the path runs behind the C ABI
+    (esmk_allgather_logits = ncclAllGather + packed-order row gather).  torch.distributed is only used to hand the
+    128-byte NCCL unique id from rank 0 to the other ranks."""
+
+    def __init__(self, group=None, device=None):
+        from . import _lib as L
+        self.L = L
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device(device)
+        buf = (C.c_char * 128)()
+        if self.rank == 0:
+            L.check(L.lib.esmk_comm_unique_id(buf), 'esmk_comm_unique_id')
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = C.create_string_buffer(box[0], 128)
+        self.handle = L.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.esmk_comm_create(C.byref(self.handle), self.world, self.rank, idbuf), 'esmk_comm_create')
+
+    def allgather_rows(self, local: torch.Tensor, perm: torch.Tensor, gathered: torch.Tensor, out: torch.Tensor):
+        L = self.L
+        t_max, V = local.shape
+        with torch.cuda.device(self.device):
+            L.check(L.lib.esmk_allgather_logits(self.handle, local.data_ptr(), t_max, V, perm.data_ptr(), out.shape[0],
+                                                gathered.data_ptr(), out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), 'esmk_allgather_logits')
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.L.lib.esmk_comm_destroy(self.handle)
+        except Exception:
+            pass
 
 
 def sequence_cost(length: int, embed_dim: int, ffn_factor: float = 24.0) -> float:
@@ -74,6 +113,7 @@ class ShardPlan:
             perm[s[3]] = torch.arange(s[3].numel(), dtype=torch.int64) + r * self.t_max
         self.perm = perm.to(device)
         self._local = self._gathered = None
+        self.comm: Optional[EsmkComm] = None      # created on the first CUDA gather (collective over the group)
 
     def gather(self, out: torch.Tensor, group=None) -> torch.Tensor:
         """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank."""
@@ -82,7 +122,13 @@ class ShardPlan:
             self._local = torch.zeros(self.t_max, width, dtype=out.dtype, device=self.device)
             self._gathered = torch.empty(self.world * self.t_max, width, dtype=out.dtype, device=self.device)
         self._local[:out.shape[0]] = out
-        dist.all_gather_into_tensor(self._gathered, self._local, group=group)      # the only collective of the path
+        if out.is_cuda and out.dtype == torch.bfloat16 and os.environ.get('ESMK_COLLECTIVE', 'esmk') != 'torch':
+            # the only collective of the path, behind the C ABI: ncclAllGather + packed-order row gather in libesmk
+            if self.comm is None:
+                self.comm = EsmkComm(group, self.device)
+            result = torch.empty(self.T, width, dtype=out.dtype, device=self.device)
+            return self.comm.allgather_rows(self._local, self.perm, self._gathered, result)
+        dist.all_gather_into_tensor(self._gathered, self._local, group=group)      # (CPU / gloo tests, ESMK_COLLECTIVE=torch)
         return self._gathered.index_select(0, self.perm)
 
 

@@ -251,6 +251,25 @@ ESMK_API int esmk_forward(esmk_model_t* m, const int64_t* tokens, const int32_t*
 ESMK_API int esmk_lm_head(esmk_model_t* m, const void* x, int T, void* workspace, size_t workspace_bytes, int output_kind,
                  void* out, esmk_stream_t stream);
 
+/* ---- multi-GPU: the one collective of the path ------------------------------- */
+/* Sequences are independent, so a packed batch is split by whole sequences over the ranks (host-side partition,
+ * esme/parallel.py), every rank runs esmk_forward on its share with replicated weights, and ONE collective -- an
+ * NCCL all-gather of the per-rank logits, padded to t_max rows -- followed by a row gather restores the original
+ * packed order on every rank.  (The reference has no multi-GPU inference path)
+ * NCCL is bound at run time (libnccl.so.2; override with ESMK_NCCL_LIB), one communicator per process / GPU.
+ *   esmk_comm_unique_id : rank 0 fills 128 bytes, the caller distributes them (torch.distributed store, MPI, a file)
+ *   esmk_comm_create    : collective over all ranks, on the calling thread's current device
+ *   esmk_allgather_logits: local [t_max, V] bf16 (rows beyond the rank's own tokens are don't-care) ->
+ *       gathered [world * t_max, V] (scratch) -> out [T, V] with out[t] = gathered[perm[t]]; perm int64[T] on the
+ *       device, perm[t] = owner_rank(t) * t_max + row of token t inside the owner's share.  out / perm may be NULL
+ *       to stop after the all-gather. */
+typedef struct esmk_comm esmk_comm_t;
+ESMK_API int esmk_comm_unique_id(void* id128);
+ESMK_API int esmk_comm_create(esmk_comm_t** out, int world_size, int rank, const void* id128);
+ESMK_API void esmk_comm_destroy(esmk_comm_t* comm);
+ESMK_API int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_max, int V, const int64_t* perm, int T,
+                                   void* gathered, void* out, esmk_stream_t stream);
+
 /* ---- per-kernel-family device timing (measurement only) ------------------------- */
 enum esmk_prof_category {
   ESMK_PROF_MISC = 0,          /* batch metadata, rope tables, embedding gather */
