@@ -9,6 +9,7 @@ needed inside the forward.
 """
 import ctypes as C
 import os
+import sys
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
@@ -32,8 +33,17 @@ class EsmkComm:
         dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         idbuf = C.create_string_buffer(box[0], 128)
         self.handle = L.c_void_p()
-        with torch.cuda.device(self.device):
-            L.check(L.lib.esmk_comm_create(C.byref(self.handle), self.world, self.rank, idbuf), 'esmk_comm_create')
+        # NCCL prints its version banner on stdout when a communicator is created outside torch (NCCL_DEBUG=WARN /
+        # VERSION environments): keep stdout clean for callers that parse it (bench.py prints one JSON line)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            with torch.cuda.device(self.device):
+                L.check(L.lib.esmk_comm_create(C.byref(self.handle), self.world, self.rank, idbuf), 'esmk_comm_create')
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def allgather_rows(self, local: torch.Tensor, perm: torch.Tensor, gathered: torch.Tensor, out: torch.Tensor):
         L = self.L
