@@ -29,7 +29,8 @@
 // pipes and the issue slots saturate at the same time as the MUFU unit; it is compiled in
 // behind ESMK_ATTN_POLY for A/B runs and off by default.
 //
-// attn_generic_kernel: CUDA-core kernel for other head dims (e.g. ESM2-8M, hd=16) and the on-device
+// The same template runs head_dim 128 (ESM2-15B): two 64-column TMA boxes per tile, 512 TMEM columns, one CTA per SM.
+// attn_generic_kernel: CUDA-core kernel for other head dims at the operator-level entry and the on-device
 // cross-check of the tcgen05 kernel.
 //
 // Semantics follow flash_attn_varlen_func as called at esme/attention.py:115-123: scale hd^-0.5, fp32
@@ -160,8 +161,11 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&s)[32], int kv_valid
 #define ARRIVE(bar) mbar_arrive_relaxed(bar)
 #endif
 
-template <int POLY>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// HD = 64: two CTAs per SM (256 TMEM columns, 98 KB smem).  HD = 128 (ESM2-15B geometry): Q / K / V tiles are two
+// 64-column TMA boxes side by side (2 x 16 KB, each SWIZZLE_128B), S = Q K^T runs 8 K-steps, P.V two N = 64 MMAs per
+// 16-key step into O [192, 320) -> 512 TMEM columns, 194 KB smem, one CTA per SM.
+template <int POLY, int HD>
+__global__ void __launch_bounds__(AT_THREADS, HD == 64 ? 2 : 1)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
               const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
@@ -180,12 +184,15 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int head0 = blockIdx.x * heads_per_cta;
   const int nh = min(heads_per_cta, H - head0);
 
+  constexpr int HALVES = HD / 64;                   // 64-column (128-byte) TMA boxes per tile row
+  constexpr int TILE_BYTES = TILE * HD * 2;
+  constexpr int HALF_BYTES = TILE * 64 * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                  // 2 stages (one per head in flight)
-  uint8_t* sK = sQ + 2 * Q_BYTES;      // 2 stages
-  uint8_t* sV = sK + 2 * Q_BYTES;      // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Q_BYTES);
+  uint8_t* sK = sQ + 2 * TILE_BYTES;      // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TILE_BYTES);
   uint64_t* q_full = bars + 0;   // [2]
   uint64_t* q_empty = bars + 2;  // [2]
   uint64_t* k_full = bars + 4;   // [2]
@@ -222,7 +229,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    tmem_alloc(tmem_slot, HD == 64 ? 256 : 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -241,28 +248,34 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     if (elect_one()) {
       int it = 0;
       for (int hi = 0; hi < nh; ++hi) {
-        const int col = (head0 + hi) * HD64;
+        const int col = (head0 + hi) * HD;
         const int qs = hi & 1;
         mbar_wait_backoff(&q_empty[qs], ((hi >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[qs], Q_BYTES);
-        tma_load_2d(sQ + qs * Q_BYTES, &tmQ, &q_full[qs], col, seq_start + q0);
+        mbar_arrive_expect_tx(&q_full[qs], TILE_BYTES);
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h)
+          tma_load_2d(sQ + qs * TILE_BYTES + h * HALF_BYTES, &tmQ, &q_full[qs], col + 64 * h, seq_start + q0);
         for (int j = 0; j < n_kv; ++j, ++it) {
           const int st = it & 1;
           const uint32_t ph = (it >> 1) & 1;
           const int krow = seq_start + j * TILE;
           mbar_wait_backoff(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], Q_BYTES);
-          tma_load_2d(sK + st * Q_BYTES, &tmK, &k_full[st], col, krow);
+          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h)
+            tma_load_2d(sK + st * TILE_BYTES + h * HALF_BYTES, &tmK, &k_full[st], col + 64 * h, krow);
           mbar_wait_backoff(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], Q_BYTES);
-          tma_load_2d(sV + st * Q_BYTES, &tmV, &v_full[st], col, krow);
+          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h)
+            tma_load_2d(sV + st * TILE_BYTES + h * HALF_BYTES, &tmV, &v_full[st], col + 64 * h, krow);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, HD64, 0, 1);   // P V   : P from TMEM, V MN-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, 64, 0, 1);     // P V   : P from TMEM, V MN-major
       // the last key block of a sequence is trimmed to its valid keys rounded up to 16: N of the S MMA and the
       // number of K steps of the P.V MMA (the softmax warps skip the same columns)
       auto issue_s = [&](int qs, int blk, int j) {                      // S = Q[qs] . K[blk & 1]^T, key block j
@@ -270,10 +283,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int n_keys = min(TILE, ((L - j * TILE) + 15) & ~15);
         const uint32_t idesc_s = make_idesc_bf16(TILE, n_keys, 0, 0);   // Q K^T : both K-major from smem
         tc_fence_after();
-        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * Q_BYTES), 16, 1024, 2);
-        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * Q_BYTES), 16, 1024, 2);
+        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * TILE_BYTES), 16, 1024, 2);
+        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * TILE_BYTES), 16, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < HD64 / 16; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k) {          // 16 head-dim elements per step; 4 steps per 64-column box
+          const uint32_t off = (k >> 2) * (HALF_BYTES >> 4) + 2 * (k & 3);
+          umma_ss(tmem_S, qdesc + off, kdesc + off, idesc_s, k != 0);
+        }
         umma_commit(s_full);
         umma_commit(&k_empty[st]);
       };
@@ -309,10 +325,12 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           TRACE_STAMP(4);
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
-          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * Q_BYTES), 1024, 1024, 2);
+          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * TILE_BYTES), 1024, 1024, 2);
           const int k_steps = min(TILE / 16, ((L - j * TILE) + 15) >> 4);
           for (int k = 0; k < k_steps; ++k)     // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
-            umma_ts(tmem_O, tmem_P + 8 * k, vdesc + (k * 2048 >> 4), idesc_o, (j | k) != 0);
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h)    // (head_dim 128: one N = 64 MMA per 64-column box of V)
+              umma_ts(tmem_O + 64 * h, tmem_P + 8 * k, vdesc + h * (HALF_BYTES >> 4) + (k * 2048 >> 4), idesc_o, (j | k) != 0);
           umma_commit(o_done);
           umma_commit(&v_empty[st]);
           TRACE_STAMP(5);
@@ -390,7 +408,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
               o_waited = true;
               tc_fence_after();
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
+              for (int h = 0; h < HD / 16; ++h) {
                 uint32_t o[16];
                 tmem_ld16(tO + h * 16, o);
                 tmem_wait_ld();
@@ -455,29 +473,35 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const float inv = 1.0f / l_sum;
       mbar_wait(o_done, (it - 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tO, o0);
-      tmem_ld32(tO + 32, o1);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
-      if (rows_ok && q0 + r < L) {
-        __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD64;
+      const bool store = rows_ok && q0 + r < L;
+      __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dst + i) = make_uint4(
-              pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+      for (int hh = 0; hh < HALVES; ++hh) {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tO + 64 * hh, o0);
+        tmem_ld32(tO + 64 * hh + 32, o1);
+        tmem_wait_ld();
+        if (hh == HALVES - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
+        }
+        if (store) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(dst + 32 + i) = make_uint4(
-              pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(dst + 64 * hh + i) = make_uint4(
+                pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(dst + 64 * hh + 32 + i) = make_uint4(
+                pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
+        }
       }
     }
   }
@@ -486,7 +510,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    tmem_dealloc(tmem_base, HD == 64 ? 256 : 512);
   }
   if (cta_trace != nullptr && threadIdx.x == 0) {
     uint32_t smid;
@@ -669,7 +693,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
   // scale_hd: the model's true head_dim when the heads were zero-padded to `hd` (softmax scale = scale_hd^-0.5)
   const float scale_log2 = (1.0f / sqrtf((float)(scale_hd > 0 ? scale_hd : hd))) * 1.4426950408889634f;
-  if (hd == 64 && impl == 0) {
+  if ((hd == 64 || hd == 128) && impl == 0) {
     ESMK_REQUIRE(tile_info != nullptr, "tile_info (esmk_batch_meta) required");
     ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");
     CUtensorMap tq, tk, tv;
@@ -678,14 +702,16 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
     using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
                               float, long long*, long long*);
-    static const kernel_t kernel = [] {         // ESMK_ATTN_POLY=1: 3/8 of the exponentials on the FMA pipes (A/B runs)
+    static const kernel_t kernel64 = [] {       // ESMK_ATTN_POLY=1: 3/8 of the exponentials on the FMA pipes (A/B runs)
       const char* e = getenv("ESMK_ATTN_POLY");
-      return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0> : attn64_kernel<3>;
+      return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0, 64> : attn64_kernel<3, 64>;
     }();
-    static std::atomic<uint64_t> configured{0};                       // per device: a process may use several GPUs
-    if (needs_config(configured)) {
-      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-      mark_configured(configured);
+    const kernel_t kernel = hd == 64 ? kernel64 : attn64_kernel<0, 128>;
+    const int smem_bytes = hd == 64 ? AT_SMEM : 2 * AT_SMEM;
+    static std::atomic<uint64_t> configured[2] = {{0}, {0}};           // per device: a process may use several GPUs
+    if (needs_config(configured[hd == 128])) {
+      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      mark_configured(configured[hd == 128]);
     }
     // log2 units by which a row maximum may outgrow the reference its P values are scaled with before O is rescaled.
     // 0 = the exact running maximum of FlashAttention-2.  Measured (tools/attn_ab.py: rms-relative error against the
@@ -709,7 +735,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     const int n_tiles = tile_capacity(T, B);
     for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
       dim3 grid((H + hpc - 1) / hpc, std::min(65535, n_tiles - t0));
-      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
+      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), smem_bytes, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
                            reinterpret_cast<const int4*>(tile_info) + t0, H, hpc, scale_log2, threshold,
                            (long long*)nullptr, (long long*)nullptr));
       if (t0 > 0) count_launch();

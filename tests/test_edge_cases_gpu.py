@@ -98,3 +98,16 @@ def test_esmc_ragged_against_oracle():
     _, rms_new, cos_new, _ = err_stats(got, exact)
     _, rms_orc, _, _ = err_stats(want, exact)
     assert rms_new <= 1.5 * rms_orc + 1e-3 and cos_new >= 0.9999
+
+
+def test_head_dim_128_model_matches_oracle():
+    """ESM2-15B geometry in miniature (embed_dim 256, 2 heads -> head_dim 128): stand-alone rotary kernel + the
+    tcgen05 attention kernel's head_dim-128 instantiation, against the oracle."""
+    model, cfg, W = _tiny('esm2', layers=2, D=256, H=2, seed=8)
+    tokens, cu, max_len = synthetic.synthetic_batch([130, 5, 64, 300], seed=14)
+    got = model(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    exact = O.forward_packed(cfg, W, tokens, cu, max_len, 'fp64').float()
+    want = O.forward_packed(cfg, W, tokens, cu, max_len, 'bf16').float()
+    _, rms_new, cos_new, _ = err_stats(got, exact)
+    _, rms_orc, _, _ = err_stats(want, exact)
+    assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new >= 0.9999

@@ -175,3 +175,39 @@ def test_unpad_and_pad_kernels_match_torch():
         want = torch.zeros(B * S, 64, dtype=torch.bfloat16)
         want[want_idx] = x
         assert torch.equal(full, want)
+
+
+def test_attention_head_dim_128_tcgen05_matches_cuda_core_and_exact():
+    """head_dim 128 (ESM2-15B geometry) on the tcgen05 kernel -- two 64-column TMA boxes per tile, 8 K-steps for
+    Q K^T, two N = 64 P.V MMAs per 16 keys, 512 TMEM columns -- against the CUDA-core kernel and the exact fp64
+    attention; ragged lengths incl. a 1-token and a > 1024-token sequence."""
+    import torch
+    from esme import ops
+    from oracle import esm_oracle as O
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(17)
+    H, hd, lens = 3, 128, [130, 1, 64, 513, 1100, 257]
+    T, D = sum(lens), H * hd
+    qkv = torch.randn(T, 3 * D, generator=g)
+    qkv[:, :2 * D] *= 1.2
+    qkv = qkv.bfloat16()
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().reshape(T, H, hd) for i in range(3))
+    exact = O.varlen_attention(q, k, v, cu, O._Prec('fp64')).reshape(T, D)
+    orc = O.varlen_attention(q.float(), k.float(), v.float(), cu, O._Prec('bf16')).reshape(T, D)
+    qd = qkv.to(dev)
+    a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    got = ops.attn_varlen(a, b, c, cu.to(dev), max(lens)).float().cpu()
+    gen = ops.attn_varlen(a, b, c, cu.to(dev), max(lens), impl=1).float().cpu()
+
+    def rel(x, y):
+        return ((x.double() - y.double()).pow(2).mean().sqrt() / y.double().pow(2).mean().sqrt()).item()
+    assert torch.isfinite(got).all()
+    assert (got - gen).abs().max() <= 0.04
+    assert rel(got, exact) <= 1.05 * rel(orc, exact) and rel(gen, exact) <= 1.05 * rel(orc, exact)
+    # batch invariance: a sequence alone == inside the batch
+    s0, s1 = int(cu[3]), int(cu[4])
+    alone = ops.attn_varlen(a[s0:s1], b[s0:s1], c[s0:s1], torch.tensor([0, s1 - s0], dtype=torch.int32, device=dev),
+                            s1 - s0).float().cpu()
+    assert torch.equal(alone, got[s0:s1])
