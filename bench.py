@@ -257,7 +257,7 @@ def gpu_reference_block(args, lens, ms_step, logits_new, model_args):
                 method='predict_log_prob' if family == 'esmc' else 'forward',
                 batch={'lens': lens, 'seed': 3}), timeout=900)
             ms, kind, y_ref = info['ms_per_step'], 'real', outs.get('out')
-            what = (f'unmodified reference package (oracle/_ref/esme) + {info["attention"]}, child process on the same '
+            what = (f'unmodified reference package (oracle/_ref, byte-compiled archive) + {info["attention"]}, child process on the same '
                     f'GPU, {info["steps"]} timed forwards after {info["warmup"]} warm-up, CUDA events')
         elif family == 'esm2':
             from oracle.restated_gpu import reference_gpu_forward

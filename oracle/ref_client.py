@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def ref_available() -> bool:
-    return os.path.isfile(os.path.join(HERE, '_ref', 'esme', 'esm.py'))
+    return os.path.isfile(os.path.join(HERE, '_ref', 'esme_ref.zip'))
 
 
 def decode(a: np.ndarray) -> torch.Tensor:

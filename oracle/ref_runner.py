@@ -1,4 +1,4 @@
-"""Run the UNMODIFIED reference package (oracle/_ref/esme, see oracle/build_ref.py) in its own process.
+"""Run the UNMODIFIED reference package (oracle/_ref/esme_ref.zip, see oracle/build_ref.py) in its own process.
 TEST INFRASTRUCTURE ONLY -- used by tests/ (parity against the real reference + flash-attn on the GPU) and by
 bench.py (the reference timed beside the product: `gpu_reference` block and the `--impl reference` CPU arm).
 
@@ -36,9 +36,9 @@ ROOT = os.path.dirname(HERE)
 
 
 def _import_reference():
-    ref_root = os.path.join(HERE, '_ref')
-    if not os.path.isfile(os.path.join(ref_root, 'esme', 'esm.py')):
-        raise SystemExit('oracle/_ref/esme is absent: run `python oracle/build_ref.py` where /root/reference exists')
+    ref_root = os.path.join(HERE, '_ref', 'esme_ref.zip')        # byte-compiled reference package (zipimport)
+    if not os.path.isfile(ref_root):
+        raise SystemExit('oracle/_ref/esme_ref.zip is absent: run `python oracle/build_ref.py` where /root/reference exists')
     # the reference first, the import stubs second; the product package must not be importable from here
     sys.path[:] = [ref_root, os.path.join(HERE, 'ref_shims')] + \
         [p for p in sys.path if os.path.abspath(p or '.') not in (ROOT, os.path.join(ROOT, 'esm-efficient_b200'))]

@@ -1,4 +1,4 @@
-"""Stub of the `accelerate` package for running the UNMODIFIED reference (oracle/_ref/esme).  TEST INFRASTRUCTURE.
+"""Stub of the `accelerate` package for running the UNMODIFIED reference (oracle/_ref/esme_ref.zip).  TEST INFRASTRUCTURE.
 
 `accelerate` is not installed in this image.  The reference imports it at module level (esme/esm.py:3) and uses
 two names, both in its checkpoint loader only (esme/esm.py:363-372) -- no arithmetic goes through it:

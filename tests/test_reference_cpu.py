@@ -19,7 +19,7 @@ def test_ref_runner_reproduces_golden_and_pins_oracle():
     batch = (g['tokens'], g['cu_lens'], g['max_len'])
     info, ref = RC.run_reference(dict(device='cpu', family='esm2', num_layers=6, embed_dim=320, attention_heads=20,
                                       weights={'safetensors': ckpt}, mode='forward'), batch=batch)
-    assert '/oracle/_ref/esme/' in info['reference_file'] and 'SDPA' in info['attention']
+    assert '/oracle/_ref/esme_ref.zip/esme/' in info['reference_file'] and 'SDPA' in info['attention']
     assert torch.equal(ref['logits'], g['logits']) and torch.equal(ref['log_prob'], g['log_prob'])
     cfg, W = O.load_checkpoint(ckpt)
     exact = O.forward_packed(cfg, W, *batch, 'fp64').float()

@@ -60,7 +60,7 @@ def test_real_weights_against_reference_flash_attn(fixture):
     batch = (g['tokens'], g['cu_lens'], g['max_len'])
     info, ref = RC.run_reference(dict(device='cuda', family='esm2', num_layers=6, embed_dim=320, attention_heads=20,
                                       weights={'safetensors': ckpt}, mode='forward'), batch=batch)
-    assert 'flash_attn' in info['attention'] and '/oracle/_ref/esme/' in info['reference_file']
+    assert 'flash_attn' in info['attention'] and '/oracle/_ref/esme_ref.zip/esme/' in info['reference_file']
     model = esme.ESM.from_pretrained(ckpt, device=DEV)
     cfg, W = O.load_checkpoint(ckpt)
     exact = O.forward_packed(cfg, W, *batch, 'fp64')
