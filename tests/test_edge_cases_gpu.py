@@ -61,10 +61,13 @@ def test_many_short_sequences():
         assert torch.equal(got[a:b], alone), s
 
 
-def test_forward_is_cuda_graph_capturable_and_stream_ordered():
+@pytest.mark.parametrize('quantization', [None, '4bit'])
+def test_forward_is_cuda_graph_capturable_and_stream_ordered(quantization):
     """esmk_forward is a fixed launch sequence with no host synchronisation: it can be captured into a CUDA graph
-    (the reference's forward cannot: rotary.py:5-14 synchronises twice per layer) and replayed on new inputs."""
-    model = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors', device=DEV)
+    (the reference's forward cannot: rotary.py:5-14 synchronises twice per layer) and replayed on new inputs.
+    Quantised models fork onto a library-owned side stream (weight expansion two GEMMs ahead) and join back inside
+    the forward, which capture must follow."""
+    model = esme.ESM.from_pretrained(f'{GOLDEN}/esm2_tiny.safetensors', quantization=quantization, device=DEV)
     lens = [200, 131, 515]
     tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=8)
     tokens, cu = tokens.to(DEV), cu.to(DEV)
