@@ -435,6 +435,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st16(tP, pk);
           l_sum += exp_pack32<POLY, false>(s1, 32, scale_log2, m_ref, pk);
           tmem_st16(tP + 16, pk);
+          TRACE_STAMP(6);
           // S_{j+1} was issued when this block's S reached the registers: poll its barrier here, where the
           // latency of the poll hides behind the remaining exponentials instead of opening the next block
           s_ready = mbar_try_wait(s_full, (cur + 1) & 1);
@@ -463,7 +464,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         }
         tmem_wait_st();
-        TRACE_STAMP(6);
+        TRACE_STAMP(7);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) ARRIVE(p_full);
@@ -731,15 +732,49 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
       const int v = atoi(e);
       if (v >= 1 && v <= 8) hpc = v;
     }
+    long long* trace = nullptr;
+    int launch_smem = smem_bytes;
+#ifdef ESMK_ATTN_TRACING   // debug builds: clock64 stamps of the first CTAs (tests/trace_attn.py); ESMK_ATTN_EXTRA_SMEM
+                           // requests extra dynamic shared memory to force one CTA per SM (contention experiments)
+    const char* trace_path = getenv("ESMK_ATTN_TRACE");
+    const size_t trace_n = 16 * 2 * 64 * 8;
+    if (trace_path != nullptr) {
+      ESMK_CUDA(cudaMalloc(&trace, trace_n * sizeof(long long)));
+      ESMK_CUDA(cudaMemsetAsync(trace, 0, trace_n * sizeof(long long), st));
+    }
+    if (const char* e = getenv("ESMK_ATTN_EXTRA_SMEM")) {
+      launch_smem += atoi(e);
+      ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, launch_smem));
+    }
+#endif
     // grid.y is limited to 65,535: a longer work list is walked in several launches
     const int n_tiles = tile_capacity(T, B);
     for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
       dim3 grid((H + hpc - 1) / hpc, std::min(65535, n_tiles - t0));
-      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), smem_bytes, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
-                           reinterpret_cast<const int4*>(tile_info) + t0, H, hpc, scale_log2, threshold,
-                           (long long*)nullptr, (long long*)nullptr));
+      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), launch_smem, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
+                           reinterpret_cast<const int4*>(tile_info) + t0, H, hpc, scale_log2, threshold, trace,
+                           (long long*)nullptr));
       if (t0 > 0) count_launch();
     }
+#ifdef ESMK_ATTN_TRACING
+    if (trace != nullptr) {   // synchronous dump "cta role block s0..s7"
+      std::vector<long long> host(trace_n);
+      ESMK_CUDA(cudaStreamSynchronize(st));
+      ESMK_CUDA(cudaMemcpy(host.data(), trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(trace);
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (size_t c = 0; c < 16 * 2; ++c)
+          for (size_t b = 0; b < 64; ++b) {
+            const long long* p = &host[(c * 64 + b) * 8];
+            if (p[0] == 0 && p[3] == 0) continue;
+            fprintf(f, "%zu %zu %zu", c / 2, c % 2, b);
+            for (int k = 0; k < 8; ++k) fprintf(f, " %lld", p[k]);
+            fprintf(f, "\n");
+          }
+        fclose(f);
+      }
+    }
+#endif
   } else {
     dim3 grid((T + GEN_WARPS - 1) / GEN_WARPS, H);
     attn_generic_kernel<<<grid, GEN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,

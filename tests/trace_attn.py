@@ -20,7 +20,7 @@ torch.cuda.synchronize()
 rows = [list(map(int, l.split())) for l in open(os.environ['ESMK_ATTN_TRACE'])]
 print('records', len(rows))
 import collections
-for role, names in ((0, ['wait_s_full', 'ldtm', 'arrive+row max', 'rescale check', 'wait_o_done', 'exp+st_P']),
+for role, names in ((0, ['wait_s_full', 'ldtm', 'arrive+row max', 'rescale (+o_done wait)', 'wait_o_done', 'exp chunks 0-1', 'exp chunks 2-3 + wait_st']),
                     (1, ['wait_s_free', 'issue_S', 'wait_p_full', 'wait_v_full', 'issue_PV'])):
     acc = collections.defaultdict(list)
     per_block = []
