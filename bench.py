@@ -578,6 +578,7 @@ def main():
         result['sharded_matches_single'] = sharded_ok
         result['per_rank'] = per_rank
         result['ms_allgather_restore'] = max(p['ms_allgather_restore'] for p in per_rank)
+        result['collective'] = plan.collective
     print(json.dumps(result))
     if world > 1:
         dist.barrier()

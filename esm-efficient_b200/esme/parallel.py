@@ -124,6 +124,7 @@ class ShardPlan:
         self.perm = perm.to(device)
         self._local = self._gathered = None
         self.comm: Optional[EsmkComm] = None      # created on the first CUDA gather (collective over the group)
+        self.collective = None                    # which implementation ran the collective (reported by bench.py)
 
     def gather(self, out: torch.Tensor, group=None) -> torch.Tensor:
         """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank."""
@@ -134,10 +135,18 @@ class ShardPlan:
         self._local[:out.shape[0]] = out
         if out.is_cuda and out.dtype == torch.bfloat16 and os.environ.get('ESMK_COLLECTIVE', 'esmk') != 'torch':
             # the only collective of the path, behind the C ABI: ncclAllGather + packed-order row gather in libesmk
-            if self.comm is None:
-                self.comm = EsmkComm(group, self.device)
-            result = torch.empty(self.T, width, dtype=out.dtype, device=self.device)
-            return self.comm.allgather_rows(self._local, self.perm, self._gathered, result)
+            if self.comm is None and self.collective is None:
+                try:
+                    self.comm = EsmkComm(group, self.device)
+                    self.collective = 'esmk_allgather_logits (ncclAllGather + row gather in libesmk, C ABI)'
+                except Exception as e:      # e.g. no loadable libnccl.so.2: every rank fails alike (same image)
+                    print(f'esme.parallel: libesmk communicator unavailable ({e}); using torch.distributed NCCL', file=sys.stderr)
+                    self.collective = 'torch.distributed.all_gather_into_tensor (NCCL) + index_select'
+            if self.comm is not None:
+                result = torch.empty(self.T, width, dtype=out.dtype, device=self.device)
+                return self.comm.allgather_rows(self._local, self.perm, self._gathered, result)
+        if self.collective is None:
+            self.collective = 'torch.distributed.all_gather_into_tensor + index_select'
         dist.all_gather_into_tensor(self._gathered, self._local, group=group)      # (CPU / gloo tests, ESMK_COLLECTIVE=torch)
         return self._gathered.index_select(0, self.perm)
 
