@@ -29,7 +29,8 @@
 // pipes and the issue slots saturate at the same time as the MUFU unit; it is compiled in
 // behind ESMK_ATTN_POLY for A/B runs and off by default.
 //
-// The same template runs head_dim 128 (ESM2-15B): two 64-column TMA boxes per tile, 512 TMEM columns, one CTA per SM.
+// The same template runs head_dim 128 (ESM2-15B: two 64-column TMA boxes per tile, 512 TMEM columns, one CTA per SM)
+// and head_dim 16 / 32 (ESM2-8M / 150M: one narrow box per head, SWIZZLE_32B / 64B, on the compact q, k, v layout).
 // attn_generic_kernel: CUDA-core kernel for other head dims at the operator-level entry and the on-device
 // cross-check of the tcgen05 kernel.
 //
@@ -165,7 +166,7 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&s)[32], int kv_valid
 // 64-column TMA boxes side by side (2 x 16 KB, each SWIZZLE_128B), S = Q K^T runs 8 K-steps, P.V two N = 64 MMAs per
 // 16-key step into O [192, 320) -> 512 TMEM columns, 194 KB smem, one CTA per SM.
 template <int POLY, int HD>
-__global__ void __launch_bounds__(AT_THREADS, HD == 64 ? 2 : 1)
+__global__ void __launch_bounds__(AT_THREADS, HD <= 64 ? 2 : 1)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
               const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
@@ -184,9 +185,16 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int head0 = blockIdx.x * heads_per_cta;
   const int nh = min(heads_per_cta, H - head0);
 
-  constexpr int HALVES = HD / 64;                   // 64-column (128-byte) TMA boxes per tile row
+  // A tile row is HD bf16 values, moved as TMA boxes of BOX columns: 64 (128-byte rows, SWIZZLE_128B; two boxes side
+  // by side for head_dim 128) or the whole head for head_dim 16 / 32 (32- / 64-byte rows, SWIZZLE_32B / 64B).
+  constexpr int BOX = HD < 64 ? HD : 64;
+  constexpr int HALVES = HD / BOX;                  // boxes per tile row
+  constexpr int ROW_BYTES = BOX * 2;
   constexpr int TILE_BYTES = TILE * HD * 2;
-  constexpr int HALF_BYTES = TILE * 64 * 2;
+  constexpr int HALF_BYTES = TILE * ROW_BYTES;      // one box
+  constexpr uint32_t SWZ = ROW_BYTES == 128 ? 2u : (ROW_BYTES == 64 ? 4u : 6u);   // UMMA descriptor layout type
+  constexpr uint32_t SBO = 8 * ROW_BYTES;           // 8-row swizzle atom
+  constexpr int KSTEPS_PER_BOX = BOX / 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                  // 2 stages (one per head in flight)
@@ -229,7 +237,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, HD == 64 ? 256 : 512);
+    tmem_alloc(tmem_slot, HD <= 64 ? 256 : 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -254,7 +262,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_arrive_expect_tx(&q_full[qs], TILE_BYTES);
 #pragma unroll
         for (int h = 0; h < HALVES; ++h)
-          tma_load_2d(sQ + qs * TILE_BYTES + h * HALF_BYTES, &tmQ, &q_full[qs], col + 64 * h, seq_start + q0);
+          tma_load_2d(sQ + qs * TILE_BYTES + h * HALF_BYTES, &tmQ, &q_full[qs], col + BOX * h, seq_start + q0);
         for (int j = 0; j < n_kv; ++j, ++it) {
           const int st = it & 1;
           const uint32_t ph = (it >> 1) & 1;
@@ -263,19 +271,19 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
 #pragma unroll
           for (int h = 0; h < HALVES; ++h)
-            tma_load_2d(sK + st * TILE_BYTES + h * HALF_BYTES, &tmK, &k_full[st], col + 64 * h, krow);
+            tma_load_2d(sK + st * TILE_BYTES + h * HALF_BYTES, &tmK, &k_full[st], col + BOX * h, krow);
           mbar_wait_backoff(&v_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
 #pragma unroll
           for (int h = 0; h < HALVES; ++h)
-            tma_load_2d(sV + st * TILE_BYTES + h * HALF_BYTES, &tmV, &v_full[st], col + 64 * h, krow);
+            tma_load_2d(sV + st * TILE_BYTES + h * HALF_BYTES, &tmV, &v_full[st], col + BOX * h, krow);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, 64, 0, 1);     // P V   : P from TMEM, V MN-major
+      constexpr uint32_t idesc_o = make_idesc_bf16(TILE, BOX, 0, 1);   // P V   : P from TMEM, V MN-major
       // the last key block of a sequence is trimmed to its valid keys rounded up to 16: N of the S MMA and the
       // number of K steps of the P.V MMA (the softmax warps skip the same columns)
       auto issue_s = [&](int qs, int blk, int j) {                      // S = Q[qs] . K[blk & 1]^T, key block j
@@ -283,11 +291,11 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int n_keys = min(TILE, ((L - j * TILE) + 15) & ~15);
         const uint32_t idesc_s = make_idesc_bf16(TILE, n_keys, 0, 0);   // Q K^T : both K-major from smem
         tc_fence_after();
-        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * TILE_BYTES), 16, 1024, 2);
-        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * TILE_BYTES), 16, 1024, 2);
+        const uint64_t qdesc = make_smem_desc(smem_u32(sQ + qs * TILE_BYTES), 16, SBO, SWZ);
+        const uint64_t kdesc = make_smem_desc(smem_u32(sK + st * TILE_BYTES), 16, SBO, SWZ);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {          // 16 head-dim elements per step; 4 steps per 64-column box
-          const uint32_t off = (k >> 2) * (HALF_BYTES >> 4) + 2 * (k & 3);
+        for (int k = 0; k < HD / 16; ++k) {          // 16 head-dim elements (32 bytes) per step, box by box
+          const uint32_t off = (k / KSTEPS_PER_BOX) * (HALF_BYTES >> 4) + 2 * (k % KSTEPS_PER_BOX);
           umma_ss(tmem_S, qdesc + off, kdesc + off, idesc_s, k != 0);
         }
         umma_commit(s_full);
@@ -325,12 +333,13 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           TRACE_STAMP(4);
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
-          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * TILE_BYTES), 1024, 1024, 2);
+          const uint64_t vdesc = make_smem_desc(smem_u32(sV + st * TILE_BYTES), SBO, SBO, SWZ);
           const int k_steps = min(TILE / 16, ((L - j * TILE) + 15) >> 4);
           for (int k = 0; k < k_steps; ++k)     // 16 keys: 8 packed P columns, 16 V rows (2048 bytes)
 #pragma unroll
-            for (int h = 0; h < HALVES; ++h)    // (head_dim 128: one N = 64 MMA per 64-column box of V)
-              umma_ts(tmem_O + 64 * h, tmem_P + 8 * k, vdesc + h * (HALF_BYTES >> 4) + (k * 2048 >> 4), idesc_o, (j | k) != 0);
+            for (int h = 0; h < HALVES; ++h)    // one N = BOX MMA per box of V; 16 keys = 16 rows of the box
+              umma_ts(tmem_O + BOX * h, tmem_P + 8 * k, vdesc + h * (HALF_BYTES >> 4) + (k * 16 * ROW_BYTES >> 4), idesc_o,
+                      (j | k) != 0);
           umma_commit(o_done);
           umma_commit(&v_empty[st]);
           TRACE_STAMP(5);
@@ -476,32 +485,53 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_after();
       const bool store = rows_ok && q0 + r < L;
       __nv_bfloat16* dst = out + (size_t)(seq_start + q0 + r) * ldo + (head0 + hi) * HD;
+      if constexpr (HD >= 64) {
 #pragma unroll
-      for (int hh = 0; hh < HALVES; ++hh) {
-        uint32_t o0[32], o1[32];
-        tmem_ld32(tO + 64 * hh, o0);
-        tmem_ld32(tO + 64 * hh + 32, o1);
-        tmem_wait_ld();
-        if (hh == HALVES - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
+        for (int hh = 0; hh < HALVES; ++hh) {
+          uint32_t o0[32], o1[32];
+          tmem_ld32(tO + 64 * hh, o0);
+          tmem_ld32(tO + 64 * hh + 32, o1);
+          tmem_wait_ld();
+          if (hh == HALVES - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ARRIVE(o_free);                // the next head's first P.V may overwrite O
+          }
+          if (store) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              *reinterpret_cast<uint4*>(dst + 64 * hh + i) = make_uint4(
+                  pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
+                  pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
+                  pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
+                  pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              *reinterpret_cast<uint4*>(dst + 64 * hh + 32 + i) = make_uint4(
+                  pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
+                  pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
+                  pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
+                  pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
+          }
         }
+      } else {                                            // head_dim 16 / 32: HD / 16 chunks of 16 columns
+        uint32_t o[HD / 16][16];
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) tmem_ld16(tO + 16 * c, o[c]);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ARRIVE(o_free);
         if (store) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(dst + 64 * hh + i) = make_uint4(
-                pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+          for (int c = 0; c < HD / 16; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(dst + 64 * hh + 32 + i) = make_uint4(
-                pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
+            for (int i = 0; i < 16; i += 8)
+              *reinterpret_cast<uint4*>(dst + 16 * c + i) = make_uint4(
+                  pack_bf16(__uint_as_float(o[c][i]) * inv, __uint_as_float(o[c][i + 1]) * inv),
+                  pack_bf16(__uint_as_float(o[c][i + 2]) * inv, __uint_as_float(o[c][i + 3]) * inv),
+                  pack_bf16(__uint_as_float(o[c][i + 4]) * inv, __uint_as_float(o[c][i + 5]) * inv),
+                  pack_bf16(__uint_as_float(o[c][i + 6]) * inv, __uint_as_float(o[c][i + 7]) * inv));
         }
       }
     }
@@ -511,7 +541,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, HD == 64 ? 256 : 512);
+    tmem_dealloc(tmem_base, HD <= 64 ? 256 : 512);
   }
   if (cta_trace != nullptr && threadIdx.x == 0) {
     uint32_t smid;
@@ -694,25 +724,28 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
   ESMK_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "q/k/v/out pitches must be multiples of 8");
   // scale_hd: the model's true head_dim when the heads were zero-padded to `hd` (softmax scale = scale_hd^-0.5)
   const float scale_log2 = (1.0f / sqrtf((float)(scale_hd > 0 ? scale_hd : hd))) * 1.4426950408889634f;
-  if ((hd == 64 || hd == 128) && impl == 0) {
+  if ((hd == 16 || hd == 32 || hd == 64 || hd == 128) && impl == 0) {
     ESMK_REQUIRE(tile_info != nullptr, "tile_info (esmk_batch_meta) required");
     ESMK_REQUIRE((reinterpret_cast<uintptr_t>(tile_info) & 15) == 0, "tile_info must be 16-byte aligned");
     CUtensorMap tq, tk, tv;
-    ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
-    ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
-    ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, HD64, 128));
+    const int box = hd < 64 ? hd : 64;        // TMA box = one head (hd 16 / 32: 32- / 64-byte rows) or 64 columns
+    ESMK_TRY(make_tmap_2d(&tq, q, T, (uint64_t)H * hd, ld, TILE, box, 2 * box));
+    ESMK_TRY(make_tmap_2d(&tk, k, T, (uint64_t)H * hd, ld, TILE, box, 2 * box));
+    ESMK_TRY(make_tmap_2d(&tv, v, T, (uint64_t)H * hd, ld, TILE, box, 2 * box));
     using kernel_t = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, __nv_bfloat16*, int, const int4*, int, int, float,
                               float, long long*, long long*);
     static const kernel_t kernel64 = [] {       // ESMK_ATTN_POLY=1: 3/8 of the exponentials on the FMA pipes (A/B runs)
       const char* e = getenv("ESMK_ATTN_POLY");
       return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0, 64> : attn64_kernel<3, 64>;
     }();
-    const kernel_t kernel = hd == 64 ? kernel64 : attn64_kernel<0, 128>;
-    const int smem_bytes = hd == 64 ? AT_SMEM : 2 * AT_SMEM;
-    static std::atomic<uint64_t> configured[2] = {{0}, {0}};           // per device: a process may use several GPUs
-    if (needs_config(configured[hd == 128])) {
+    const int variant = hd == 64 ? 0 : (hd == 128 ? 1 : (hd == 32 ? 2 : 3));
+    const kernel_t kernel = hd == 64 ? kernel64
+                          : hd == 128 ? attn64_kernel<0, 128> : (hd == 32 ? attn64_kernel<0, 32> : attn64_kernel<0, 16>);
+    const int smem_bytes = TILE * hd * 2 * 6 + 1024 + 192;             // Q, K, V double-buffered + barriers + alignment
+    static std::atomic<uint64_t> configured[4] = {{0}, {0}, {0}, {0}}; // per device: a process may use several GPUs
+    if (needs_config(configured[variant])) {
       ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      mark_configured(configured[hd == 128]);
+      mark_configured(configured[variant]);
     }
     // log2 units by which a row maximum may outgrow the reference its P values are scaled with before O is rescaled.
     // 0 = the exact running maximum of FlashAttention-2.  Measured (tools/attn_ab.py: rms-relative error against the

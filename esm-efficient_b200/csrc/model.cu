@@ -125,7 +125,7 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len, size_t 
   b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;     // two scratch weights: one being read by a GEMM,
   b.wq2 = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;    // one being expanded for the GEMM after next
   // small head dims: heads zero-padded to 64 columns for the tcgen05 attention kernel (see pad_heads)
-  const bool pad = hd < 64;
+  const bool pad = hd < 64 && hd != 16 && hd != 32;    // (hd 16 / 32 run the tcgen05 kernel on the compact layout)
   b.qkvp = pad ? w.take<__nv_bfloat16>((size_t)T * 3 * c.attention_heads * 64) : nullptr;
   b.ap = pad ? w.take<__nv_bfloat16>((size_t)T * c.attention_heads * 64) : nullptr;
   b.bytes = w.off;
@@ -342,7 +342,7 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
         PROF(ESMK_PROF_ROPE, qk_norm_rope(b.qkv, b.qkv + D, 3 * D, T, H, hd, l.qln_w, l.kln_w, c.no_rotary ? nullptr : b.cosb,
                                           c.no_rotary ? nullptr : b.sinb, b.pos, st));
     }
-    if (hd < 64) {
+    if (hd < 64 && hd != 16 && hd != 32) {
       const int Dp = H * 64;
       PROF(ESMK_PROF_ATTENTION, pad_heads(b.qkv, 3 * D, b.qkvp, T, 3, H, hd, st));
       PROF(ESMK_PROF_ATTENTION, attn_varlen(b.qkvp, b.qkvp + Dp, b.qkvp + 2 * Dp, 3 * Dp, b.ap, Dp, cu_lens, b.tile_info, B,

@@ -153,8 +153,8 @@ ESMK_API int esmk_gemm(const esmk_gemm_args* args, esmk_stream_t stream);
  *   q,k,v : bf16, token t / head h at  ptr + t*ld + h*hd   (e.g. three column
  *           blocks of one [T,3D] QKV GEMM output, ld = 3D)
  *   out   : bf16 [T, H*hd], pitch ldo
- *   tile_info from esmk_batch_meta (required for head_dim 64 and 128).
- * head_dim 64 and 128 run the tcgen05/TMA kernel (the whole-model entry also runs head dims < 64 through it with
+ *   tile_info from esmk_batch_meta (required for the tcgen05 kernel).
+ * head_dim 16, 32, 64 and 128 run the tcgen05/TMA kernel (the whole-model entry runs head_dim 24 through it with
  * zero-padded heads); other head dims (<= 128, multiple of 8) run a CUDA-core kernel here.
  * impl: 0 = auto, 1 = force the CUDA-core kernel. */
 ESMK_API int esmk_attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo,

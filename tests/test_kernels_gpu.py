@@ -211,3 +211,34 @@ def test_attention_head_dim_128_tcgen05_matches_cuda_core_and_exact():
     alone = ops.attn_varlen(a[s0:s1], b[s0:s1], c[s0:s1], torch.tensor([0, s1 - s0], dtype=torch.int32, device=dev),
                             s1 - s0).float().cpu()
     assert torch.equal(alone, got[s0:s1])
+
+
+@pytest.mark.parametrize('hd', [16, 32])
+def test_attention_small_head_dims_tcgen05_match_cuda_core_and_exact(hd):
+    """head_dim 16 / 32 (ESM2-8M / 150M geometry) on the tcgen05 kernel over the COMPACT q, k, v layout: one TMA box
+    per head (32- / 64-byte rows, SWIZZLE_32B / 64B), Q K^T in hd / 16 K-steps, P.V with N = hd."""
+    import torch
+    from esme import ops
+    from oracle import esm_oracle as O
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(19)
+    H, lens = 5, [130, 1, 64, 513, 700, 257, 33]
+    T, D = sum(lens), H * hd
+    qkv = torch.randn(T, 3 * D, generator=g)
+    qkv[:, :2 * D] *= 1.5
+    qkv = qkv.bfloat16()
+    cu = torch.zeros(len(lens) + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(torch.tensor(lens), 0)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].double().reshape(T, H, hd) for i in range(3))
+    exact = O.varlen_attention(q, k, v, cu, O._Prec('fp64')).reshape(T, D)
+    orc = O.varlen_attention(q.float(), k.float(), v.float(), cu, O._Prec('bf16')).reshape(T, D)
+    qd = qkv.to(dev)
+    a, b, c = (qd[:, i * D:(i + 1) * D].unflatten(1, (H, hd)) for i in range(3))
+    got = ops.attn_varlen(a, b, c, cu.to(dev), max(lens)).float().cpu()
+    gen = ops.attn_varlen(a, b, c, cu.to(dev), max(lens), impl=1).float().cpu()
+
+    def rel(x, y):
+        return ((x.double() - y.double()).pow(2).mean().sqrt() / y.double().pow(2).mean().sqrt()).item()
+    assert torch.isfinite(got).all()
+    assert (got - gen).abs().max() <= 0.04, (got - gen).abs().max()
+    assert rel(got, exact) <= 1.05 * rel(orc, exact)
