@@ -222,7 +222,7 @@ def bench_mask_margin(args, family, layers, D, H):
         score_check = {'spearman_vs_bf16': float(torch.corrcoef(torch.stack((ra, rb)))[0, 1]),
                        'mean_abs_diff_vs_bf16': float((a - b).abs().mean()), 'max_abs_diff_vs_bf16': float((a - b).abs().max()),
                        'bf16_sweep_ms': bf16_sec * 1e3, 'quantised_over_bf16_time': sec / bf16_sec}
-    print(json.dumps({
+    emit({
         'metric': 'residues_per_sec_mask_margin_sweep', 'value': 1024 * 1026 / sec, 'unit': UNIT, 'n_gpus': 1,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
@@ -230,7 +230,7 @@ def bench_mask_margin(args, family, layers, D, H):
                                f'32 packed forwards of 32 x 1,026 tokens, LM head on the 1,024 masked rows only, '
                                f'one D2H of the [1024, 20] score matrix; wall-clock incl. host-side DataFrame',
                    'rows': int(df.shape[0]), 'weights': quant_note, 'scores_vs_bf16': score_check},
-        'clocks': clocks, 'gpu_launches': launches}))
+        'clocks': clocks, 'gpu_launches': launches})
 
 
 def err_stats(a, b):
@@ -327,6 +327,28 @@ def attention_vs_flash_block(D, H, lens, dev):
         return {'unavailable': f'{type(e).__name__}: {str(e)[-300:]}'}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything libraries print on stdout from here on (NCCL's version banner, for one) goes to stderr; the ONE
+    JSON line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -346,6 +368,7 @@ def main():
                     help="'mask_margin' = BASELINE config 5: predict_mask_margin sweep over one 1,024-residue protein")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -360,7 +383,7 @@ def main():
         steps = max(1, min(args.steps, 5))
         base, sec = run_cpu_reference(args, lens, steps, 1)
         assert not any('libesmk' in l for l in open('/proc/self/maps')), 'the CPU reference arm must not map libesmk.so'
-        print(json.dumps({
+        emit({
             'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': steps, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
@@ -368,7 +391,7 @@ def main():
                                    f'bounded CPU sample: {base["sample"]}'},
             'cpu_baseline': base,
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}))
+            'gpu_launches': 0})
         return
 
     if args.workload == 'mask_margin':
@@ -579,7 +602,7 @@ def main():
         result['per_rank'] = per_rank
         result['ms_allgather_restore'] = max(p['ms_allgather_restore'] for p in per_rank)
         result['collective'] = plan.collective
-    print(json.dumps(result))
+    emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
