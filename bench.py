@@ -480,7 +480,9 @@ def main():
     ms_gather_local = 0.0
     local_logits, full_logits = step(tok_d, cu_d)
     if world > 1:
-        ms_gather_local = timed(lambda: plan.gather(local_logits), 10, reduce_max=False)
+        for _ in range(3):
+            plan.gather(local_logits)
+        ms_gather_local = timed(lambda: plan.gather(local_logits), 20, reduce_max=False)
     _lib.profile_enable(True)                      # CUDA-event pairs around every launch
     prof_steps = 3
     timed(lambda: forward(tok_d, (cu_d, max_len)), prof_steps, reduce_max=False)
