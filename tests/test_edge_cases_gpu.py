@@ -114,3 +114,35 @@ def test_head_dim_128_model_matches_oracle():
     _, rms_new, cos_new, _ = err_stats(got, exact)
     _, rms_orc, _, _ = err_stats(want, exact)
     assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new >= 0.9999
+
+
+def test_head_dim_32_model_matches_oracle():
+    """ESM2-150M geometry in miniature (embed_dim 128, 4 heads -> head_dim 32): fused QKV + RoPE epilogue and the
+    tcgen05 attention kernel's native head_dim-32 instantiation (64-byte TMA rows), against the oracle."""
+    model, cfg, W = _tiny('esm2', layers=2, D=128, H=4, seed=9)
+    tokens, cu, max_len = synthetic.synthetic_batch([130, 5, 64, 300], seed=15)
+    got = model(tokens.to(DEV), (cu.to(DEV), max_len)).float().cpu()
+    exact = O.forward_packed(cfg, W, tokens, cu, max_len, 'fp64').float()
+    want = O.forward_packed(cfg, W, tokens, cu, max_len, 'bf16').float()
+    _, rms_new, cos_new, _ = err_stats(got, exact)
+    _, rms_orc, _, _ = err_stats(want, exact)
+    assert rms_new <= 1.5 * rms_orc + 1e-4 and cos_new >= 0.9999
+
+
+def test_attention_work_list_longer_than_one_launch():
+    """More than 65,535 query tiles (here 70,000 two- and three-token sequences): the work list is walked in several
+    launches; result against the CUDA-core kernel."""
+    from esme import ops
+    g = torch.Generator().manual_seed(23)
+    B = 70000
+    lens = torch.randint(2, 4, (B,), generator=g)
+    T = int(lens.sum())
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    H, hd = 2, 64
+    qkv = torch.randn(T, 3 * H * hd, generator=g).bfloat16().to(DEV)
+    q, k, v = (qkv[:, i * H * hd:(i + 1) * H * hd].unflatten(1, (H, hd)) for i in range(3))
+    got = ops.attn_varlen(q, k, v, cu.to(DEV), 3)
+    want = ops.attn_varlen(q, k, v, cu.to(DEV), 3, impl=1)
+    assert torch.isfinite(got.float()).all()
+    assert (got.float() - want.float()).abs().max() <= 0.04
