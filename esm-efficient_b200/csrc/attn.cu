@@ -59,7 +59,6 @@ constexpr int HD64 = 64;
 constexpr int Q_BYTES = TILE * HD64 * 2;   // 16 KB
 constexpr int AT_TMEM_COLS = 256;
 constexpr int AT_THREADS = 64 + 128;         // producer warp, MMA warp, 4 softmax warps (one thread per query row)
-constexpr int AT_THREADS_CORR = 3 * 128;     // CORR: warpgroup 0 = producer, MMA, 2 idle; 1 = softmax; 2 = O rescale
 constexpr int AT_SMEM = Q_BYTES * 6 + 1024 + 192;
 constexpr int kDefaultPoly = 0;            // eighths of the exponentials on the FMA pipes (see exp_pack32): measured, no gain
 constexpr float kRescaleThreshold = 0.0f;  // log2 units (see attn_varlen for the measured accuracy / time trade-off)
@@ -166,8 +165,8 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&s)[32], int kv_valid
 // HD = 64: two CTAs per SM (256 TMEM columns, 98 KB smem).  HD = 128 (ESM2-15B geometry): Q / K / V tiles are two
 // 64-column TMA boxes side by side (2 x 16 KB, each SWIZZLE_128B), S = Q K^T runs 8 K-steps, P.V two N = 64 MMAs per
 // 16-key step into O [192, 320) -> 512 TMEM columns, 194 KB smem, one CTA per SM.
-template <int POLY, int HD, bool CORR>
-__global__ void __launch_bounds__(CORR ? AT_THREADS_CORR : AT_THREADS, HD <= 64 ? 2 : 1)
+template <int POLY, int HD>
+__global__ void __launch_bounds__(AT_THREADS, HD <= 64 ? 2 : 1)
 attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo,
               const int4* __restrict__ tile_info, int H, int heads_per_cta, float scale_log2,
@@ -213,10 +212,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* p_full = bars + 14;
   uint64_t* o_done = bars + 15;
   uint64_t* o_free = bars + 16;
-  uint64_t* alpha_ready = bars + 17;   // [4] CORR: the quadrant's 32 rescale factors of this block are in `alpha`
-  uint64_t* o_scaled = bars + 21;      // CORR: O carries the new reference, P.V of this block may accumulate
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* alpha = reinterpret_cast<float*>(bars + 24);   // CORR: [2][128] rescale factor per query row, by block parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,10 +234,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     mbar_init(p_full, 4);
     mbar_init(o_done, 1);
     mbar_init(o_free, 4);
-    if constexpr (CORR) {
-      for (int i = 0; i < 4; ++i) mbar_init(&alpha_ready[i], 1);
-      mbar_init(o_scaled, 4);
-    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -256,12 +248,9 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t tmem_P = tmem_base + 128;
   const uint32_t tmem_O = tmem_base + 192;
   const long long t_loop = cta_trace ? (long long)global_timer_ns() : 0;
-  // CORR: register file re-split by role (setmaxnreg at the head of each warpgroup's branch): 40 | 152 | 48 of the
-  // 240 per thread triple the launch grants
 
   // `it` counts key blocks across all heads of this CTA: K/V stage = it & 1, stage phase = (it >> 1) & 1,
   // and the per-block barriers (s_full, s_free, p_full, o_done) complete once per block -> parity it & 1.
-  if (CORR && warp < 4) reg_dec<40>();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
@@ -341,7 +330,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           mbar_wait_backoff(&v_full[st], (cur >> 1) & 1);
           TRACE_STAMP(3);
           mbar_wait_backoff(p_full, cur & 1);
-          if constexpr (CORR) mbar_wait_backoff(o_scaled, cur & 1);      // (completed long before P: no extra latency)
           TRACE_STAMP(4);
           if (j == 0 && hi > 0) mbar_wait_backoff(o_free, (hi - 1) & 1); // previous head's O has been read out
           tc_fence_after();
@@ -359,48 +347,12 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         it += n_kv;
       }
     }
-  } else if (CORR && warp >= 8) {
-    // ===================== CORR: O rescale warps, one thread per query row =====================
-    // The softmax thread of row r publishes f = 2^(m_old - m_new) per block; these warps apply it to the O accumulator
-    // in TMEM between P.V_{j-1} and P.V_j, off the softmax threads' critical path.
-    reg_dec<48>();
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const uint32_t tO = tmem_O + (static_cast<uint32_t>(quad * 32) << 16);
-    int it = 0;
-    for (int hi = 0; hi < nh; ++hi) {
-      for (int j = 0; j < n_kv; ++j) {
-        const int cur = it + j;
-        if (lane == 0) mbar_wait_backoff(&alpha_ready[quad], cur & 1);   // one parked lane per warp, no spinning
-        __syncwarp();
-        const float f = alpha[(cur & 1) * TILE + r];
-        if (__any_sync(0xffffffffu, f != 1.0f)) {                       // (never at j == 0: the first P.V overwrites O)
-          mbar_wait(o_done, (cur - 1) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < HD / 16; ++h) {
-            uint32_t o[16];
-            tmem_ld16(tO + h * 16, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st16(tO + h * 16, o);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-        }
-        __syncwarp();
-        if (lane == 0) ARRIVE(o_scaled);
-      }
-      it += n_kv;
-    }
-  } else if (!CORR || warp >= 4) {
+  } else {
     // ===================== softmax warps: one thread per query row =====================
     // Every instruction that goes through the SM's MIO queue (mbarrier polls, TMEM loads/stores, shared
     // memory) waits behind the MUFU ops of whichever CTA is in its exponential phase, so the per-block
     // protocol is kept to the minimum: one S wait, four TMEM loads, one arrive, one O wait, four P stores,
     // one arrive per 128 exponentials -- no cross-thread exchange of the row maximum or the row sum.
-    if constexpr (CORR) reg_inc<152>();
     const int quad = warp & 3;                 // TMEM lane quadrant (warps 2,3,4,5 -> quadrants 2,3,0,1)
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -408,7 +360,7 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tP = tmem_P + lane_off;
     const uint32_t tO = tmem_O + lane_off;
     int it = 0;
-    [[maybe_unused]] const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == (CORR ? 128 : 64));
+    [[maybe_unused]] const bool tr_on = (blockIdx.y < 16) && (blockIdx.x == 0) && (threadIdx.x == 64);
     [[maybe_unused]] long long* tr_base = trace ? trace + (size_t)blockIdx.y * 2 * 64 * 8 : nullptr;
     [[maybe_unused]] int tr_n = 0;
     // a warp whose 32 query rows all lie beyond the end of the sequence keeps the barrier protocol but skips
@@ -425,90 +377,6 @@ attn64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const bool masked = kv_valid < TILE;
         tr_n = cur;
         TRACE_STAMP(0);
-        if constexpr (CORR) {
-          // ---- CORR: the O rescale is another warpgroup's job; this thread publishes the factor and goes on ----
-          mbar_wait(s_full, cur & 1);
-          tc_fence_after();
-          TRACE_STAMP(1);
-          // S is read in halves and a second time for the exponentials: at most 64 scores live in registers (the
-          // 152-register budget of this role holds no 128), S stays in TMEM until the second read has landed
-          uint32_t s0[32], s1[32], s2[32], s3[32];
-          float mine = -INFINITY;
-          tmem_ld32(tS, s0);
-          tmem_ld32(tS + 32, s1);
-          tmem_wait_ld();
-          if (!masked) {
-            mine = fmaxf(chunk_max<false>(s0, 32), chunk_max<false>(s1, 32));
-          } else if (kv_valid > 0) {
-            mine = chunk_max<true>(s0, kv_valid);
-            if (kv_valid > 32) mine = fmaxf(mine, chunk_max<true>(s1, kv_valid - 32));
-          }
-          tmem_ld32(tS + 64, s2);
-          tmem_ld32(tS + 96, s3);
-          tmem_wait_ld();
-          TRACE_STAMP(2);
-          if (!masked) {
-            mine = fmaxf(mine, fmaxf(chunk_max<false>(s2, 32), chunk_max<false>(s3, 32)));
-          } else {
-            if (kv_valid > 64) mine = fmaxf(mine, chunk_max<true>(s2, kv_valid - 64));
-            if (kv_valid > 96) mine = fmaxf(mine, chunk_max<true>(s3, kv_valid - 96));
-          }
-          float f = 1.0f;
-          if (rows_ok) {
-            const float mx = mine * scale_log2;
-            if (j == 0) {
-              m_ref = mx;
-            } else if (mx > m_ref + rescale_threshold) {
-              f = fast_exp2(m_ref - mx);
-              l_sum *= f;
-              m_ref = mx;
-            }
-          }
-          alpha[(cur & 1) * TILE + r] = f;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&alpha_ready[quad]);   // (.release: orders the warp's factor stores)
-          TRACE_STAMP(3);
-          uint32_t pk[16];
-          if (kv_valid > 64) {
-            l_sum += masked ? exp_pack32<POLY, true>(s2, kv_valid - 64, scale_log2, m_ref, pk)
-                            : exp_pack32<POLY, false>(s2, 32, scale_log2, m_ref, pk);
-          }
-          TRACE_STAMP(4);
-          if (j > 0) {                                  // P_{j-1} must have been consumed before it is overwritten
-            mbar_wait(o_done, (cur - 1) & 1);           // (j == 0: the previous head's epilogue already waited)
-            tc_fence_after();
-          }
-          TRACE_STAMP(5);
-          if (kv_valid > 64) tmem_st16(tP + 32, pk);
-          tmem_ld32(tS, s0);
-          if (kv_valid > 96) {
-            l_sum += masked ? exp_pack32<POLY, true>(s3, kv_valid - 96, scale_log2, m_ref, pk)
-                            : exp_pack32<POLY, false>(s3, 32, scale_log2, m_ref, pk);
-            tmem_st16(tP + 48, pk);
-          }
-          tmem_ld32(tS + 32, s1);
-          tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ARRIVE(s_free);                // all 4 warps arrived -> S may be overwritten
-          TRACE_STAMP(6);
-          if (kv_valid > 0) {
-            l_sum += masked ? exp_pack32<POLY, true>(s0, kv_valid, scale_log2, m_ref, pk)
-                            : exp_pack32<POLY, false>(s0, 32, scale_log2, m_ref, pk);
-            tmem_st16(tP, pk);
-          }
-          if (kv_valid > 32) {
-            l_sum += masked ? exp_pack32<POLY, true>(s1, kv_valid - 32, scale_log2, m_ref, pk)
-                            : exp_pack32<POLY, false>(s1, 32, scale_log2, m_ref, pk);
-            tmem_st16(tP + 16, pk);
-          }
-          tmem_wait_st();
-          TRACE_STAMP(7);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ARRIVE(p_full);
-          continue;
-        }
         if (!s_ready) mbar_wait(s_full, cur & 1);
         tc_fence_after();
         TRACE_STAMP(1);
@@ -868,14 +736,12 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
                               float, long long*, long long*);
     static const kernel_t kernel64 = [] {       // ESMK_ATTN_POLY=1: 3/8 of the exponentials on the FMA pipes (A/B runs)
       const char* e = getenv("ESMK_ATTN_POLY");
-      return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0, 64, false> : attn64_kernel<3, 64, false>;
+      return (e ? atoi(e) : kDefaultPoly) <= 0 ? attn64_kernel<0, 64> : attn64_kernel<3, 64>;
     }();
-    static const bool corr = [] { const char* e = getenv("ESMK_ATTN_CORR"); return e != nullptr && e[0] == '1'; }();
-    const bool use_corr = corr && hd == 64;
     const int variant = hd == 64 ? 0 : (hd == 128 ? 1 : (hd == 32 ? 2 : 3));
-    const kernel_t kernel = use_corr ? attn64_kernel<0, 64, true> : hd == 64 ? kernel64
-                          : hd == 128 ? attn64_kernel<0, 128, false> : (hd == 32 ? attn64_kernel<0, 32, false> : attn64_kernel<0, 16, false>);
-    const int smem_bytes = TILE * hd * 2 * 6 + 1024 + 192 + (use_corr ? 1024 : 0);   // Q, K, V double-buffered + barriers + alignment (+ factors)
+    const kernel_t kernel = hd == 64 ? kernel64
+                          : hd == 128 ? attn64_kernel<0, 128> : (hd == 32 ? attn64_kernel<0, 32> : attn64_kernel<0, 16>);
+    const int smem_bytes = TILE * hd * 2 * 6 + 1024 + 192;             // Q, K, V double-buffered + barriers + alignment
     static std::atomic<uint64_t> configured[4] = {{0}, {0}, {0}, {0}}; // per device: a process may use several GPUs
     if (needs_config(configured[variant])) {
       ESMK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -918,7 +784,7 @@ int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, 
     const int n_tiles = tile_capacity(T, B);
     for (int t0 = 0; t0 < n_tiles; t0 += 65535) {
       dim3 grid((H + hpc - 1) / hpc, std::min(65535, n_tiles - t0));
-      ESMK_CUDA(launch_pdl(kernel, grid, dim3(use_corr ? AT_THREADS_CORR : AT_THREADS), launch_smem, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
+      ESMK_CUDA(launch_pdl(kernel, grid, dim3(AT_THREADS), launch_smem, st, tq, tk, tv, (__nv_bfloat16*)out, ldo,
                            reinterpret_cast<const int4*>(tile_info) + t0, H, hpc, scale_log2, threshold, trace,
                            (long long*)nullptr));
       if (t0 > 0) count_launch();
