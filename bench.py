@@ -37,6 +37,8 @@ sys.path.insert(0, os.path.join(ROOT, 'esm-efficient_b200'))
 
 MODELS = {
     'esm2_8m': ('esm2', 6, 320, 20),
+    'esm2_35m': ('esm2', 12, 480, 20),
+    'esm2_150m': ('esm2', 30, 640, 20),
     'esm2_650m': ('esm2', 33, 1280, 20),
     'esm2_3b': ('esm2', 36, 2560, 40),
     'esmc_300m': ('esmc', 30, 960, 15),

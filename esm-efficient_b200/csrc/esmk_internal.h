@@ -39,8 +39,8 @@ int dequantize(const void* data, const float* scale, int N, int K, int bits, voi
 int attn_varlen(const void* q, const void* k, const void* v, int ld, void* out, int ldo, const int32_t* cu_lens,
                 const int32_t* tile_info, int B, int T, int H, int hd, int max_len, int impl, cudaStream_t st,
                 int scale_hd = 0);
-int pad_heads(const void* src, int ld_src, void* dst, int T, int parts, int H, int hd, cudaStream_t st);
-int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, cudaStream_t st);
+int pad_heads(const void* src, int ld_src, void* dst, int T, int parts, int H, int hd, int hp, cudaStream_t st);
+int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, int hp, cudaStream_t st);
 
 int attn_pool(const void* q, int ldq, const void* k, const void* v, int ld, void* out, const int32_t* cu_lens, int B,
               int C, int H, int hd, cudaStream_t st);

@@ -124,10 +124,12 @@ Buffers carve(const esmk_config& c, void* ws, int T, int B, int max_len, size_t 
   b.tile_info = w.take<int32_t>((size_t)4 * tile_capacity(T, B));
   b.wq = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;     // two scratch weights: one being read by a GEMM,
   b.wq2 = wq_elems ? w.take<__nv_bfloat16>(wq_elems) : nullptr;    // one being expanded for the GEMM after next
-  // small head dims: heads zero-padded to 64 columns for the tcgen05 attention kernel (see pad_heads)
-  const bool pad = hd < 64 && hd != 16 && hd != 32;    // (hd 16 / 32 run the tcgen05 kernel on the compact layout)
-  b.qkvp = pad ? w.take<__nv_bfloat16>((size_t)T * 3 * c.attention_heads * 64) : nullptr;
-  b.ap = pad ? w.take<__nv_bfloat16>((size_t)T * c.attention_heads * 64) : nullptr;
+  // other small head dims (ESM2-35M: 24): heads zero-padded to the next width the tcgen05 attention kernel is
+  // instantiated for (32 or 64 columns, see pad_heads); hd 16 / 32 / 64 / 128 run it on the compact layout
+  const bool pad = hd < 64 && hd != 16 && hd != 32;
+  const int hp = hd < 32 ? 32 : 64;
+  b.qkvp = pad ? w.take<__nv_bfloat16>((size_t)T * 3 * c.attention_heads * hp) : nullptr;
+  b.ap = pad ? w.take<__nv_bfloat16>((size_t)T * c.attention_heads * hp) : nullptr;
   b.bytes = w.off;
   return b;
 }
@@ -343,11 +345,12 @@ int forward(esmk_model* m, const int64_t* tokens, const int32_t* cu_lens, int T,
                                           c.no_rotary ? nullptr : b.sinb, b.pos, st));
     }
     if (hd < 64 && hd != 16 && hd != 32) {
-      const int Dp = H * 64;
-      PROF(ESMK_PROF_ATTENTION, pad_heads(b.qkv, 3 * D, b.qkvp, T, 3, H, hd, st));
+      const int hp = hd < 32 ? 32 : 64;
+      const int Dp = H * hp;
+      PROF(ESMK_PROF_ATTENTION, pad_heads(b.qkv, 3 * D, b.qkvp, T, 3, H, hd, hp, st));
       PROF(ESMK_PROF_ATTENTION, attn_varlen(b.qkvp, b.qkvp + Dp, b.qkvp + 2 * Dp, 3 * Dp, b.ap, Dp, cu_lens, b.tile_info, B,
-                                            T, H, 64, max_len, 0, st, hd));
-      PROF(ESMK_PROF_ATTENTION, unpad_heads(b.ap, b.a, D, T, H, hd, st));
+                                            T, H, hp, max_len, 0, st, hd));
+      PROF(ESMK_PROF_ATTENTION, unpad_heads(b.ap, b.a, D, T, H, hd, hp, st));
     } else {
       PROF(ESMK_PROF_ATTENTION,
            attn_varlen(b.qkv, b.qkv + D, b.qkv + 2 * D, 3 * D, b.a, D, cu_lens, b.tile_info, B, T, H, hd, max_len, 0, st));

@@ -689,42 +689,47 @@ int residual_add(const void* x, const void* y, void* out, long n, float scale, c
 // One thread per 16-byte group of the padded row.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pad_heads_kernel(const uint4* __restrict__ src, int ld8, uint4* __restrict__ dst, long n, int heads, int hd8) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // (token, part*head, group of 8 inside 64)
+pad_heads_kernel(const uint4* __restrict__ src, int ld8, uint4* __restrict__ dst, long n, int heads, int hd8, int hp8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // (token, part*head, group of 8 inside the padded head)
   if (i >= n) return;
-  const int g = (int)(i & 7);
-  const long th = i >> 3;
+  const int g = (int)(i % hp8);
+  const long th = i / hp8;
   const int h = (int)(th % heads);
   const long t = th / heads;
   dst[i] = g < hd8 ? __ldg(src + t * ld8 + (long)h * hd8 + g) : make_uint4(0, 0, 0, 0);
 }
 
 __global__ void __launch_bounds__(256)
-unpad_heads_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ld8, long n, int heads, int hd8) {
+unpad_heads_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ld8, long n, int heads, int hd8, int hp8) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // (token, head, group of 8 inside hd)
   if (i >= n) return;
   const int g = (int)(i % hd8);
   const long th = i / hd8;
   const int h = (int)(th % heads);
   const long t = th / heads;
-  dst[t * ld8 + (long)h * hd8 + g] = __ldg(src + (t * heads + h) * 8 + g);
+  dst[t * ld8 + (long)h * hd8 + g] = __ldg(src + (t * heads + h) * hp8 + g);
 }
 
-int pad_heads(const void* src, int ld_src, void* dst, int T, int parts, int H, int hd, cudaStream_t st) {
-  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < 64 && ld_src % 8 == 0, "pad_heads: head_dim must be a multiple of 8 below 64");
-  const long n = (long)T * parts * H * 8;
+// heads of `hd` columns copied into heads of `hp` columns (hp = 32 or 64, zero fill), `parts` = q | k | v blocks per row
+int pad_heads(const void* src, int ld_src, void* dst, int T, int parts, int H, int hd, int hp, cudaStream_t st) {
+  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < hp && (hp == 32 || hp == 64) && ld_src % 8 == 0,
+               "pad_heads: head_dim must be a multiple of 8 below the padded width (32 or 64)");
+  const long n = (long)T * parts * H * (hp / 8);
   if (n == 0) return 0;
-  pad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, ld_src / 8, (uint4*)dst, n, parts * H, hd / 8);
+  pad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, ld_src / 8, (uint4*)dst, n, parts * H, hd / 8,
+                                                                  hp / 8);
   count_launch();
   ESMK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, cudaStream_t st) {
-  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < 64 && ld_dst % 8 == 0, "unpad_heads: head_dim must be a multiple of 8 below 64");
+int unpad_heads(const void* src, void* dst, int ld_dst, int T, int H, int hd, int hp, cudaStream_t st) {
+  ESMK_REQUIRE(src && dst && hd % 8 == 0 && hd < hp && (hp == 32 || hp == 64) && ld_dst % 8 == 0,
+               "unpad_heads: head_dim must be a multiple of 8 below the padded width (32 or 64)");
   const long n = (long)T * H * (hd / 8);
   if (n == 0) return 0;
-  unpad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, ld_dst / 8, n, H, hd / 8);
+  unpad_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, ld_dst / 8, n, H, hd / 8,
+                                                                    hp / 8);
   count_launch();
   ESMK_CUDA(cudaGetLastError());
   return 0;

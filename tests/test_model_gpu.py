@@ -165,8 +165,8 @@ def test_full_size_650m_properties():
 
 def test_head_dim_24_model_matches_oracle():
     """ESM2-35M geometry (embed_dim 480, 20 heads -> head_dim 24; the reference dispatches it to flash-attn's
-    hd<=32 kernel): stand-alone pair-wise rotary kernel + CUDA-core attention, against the oracle on seeded
-    synthetic weights (no 35M checkpoint exists offline)."""
+    hd<=32 kernel): stand-alone pair-wise rotary kernel + the tcgen05 attention kernel on heads zero-padded to 32
+    columns, against the oracle on seeded synthetic weights (no 35M checkpoint exists offline)."""
     from esme import synthetic
     layers, D, H = 2, 480, 20
     sd = synthetic.synthetic_state_dict('esm2', layers, D, seed=7)
