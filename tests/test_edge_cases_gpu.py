@@ -146,3 +146,24 @@ def test_attention_work_list_longer_than_one_launch():
     want = ops.attn_varlen(q, k, v, cu.to(DEV), 3, impl=1)
     assert torch.isfinite(got.float()).all()
     assert (got.float() - want.float()).abs().max() <= 0.04
+
+
+def test_batch_with_more_than_2_31_activation_elements():
+    """600k packed tokens at ESM2-650M width: T x 3D = 2.3e9 and T x F = 3.1e9 elements, beyond 32-bit indexing
+    (15 GB of activations).  First, middle and last sequence equal their stand-alone forward bit for bit."""
+    layers, D, H = 2, 1280, 20
+    sd = synthetic.synthetic_state_dict('esm2', layers, D, seed=3)
+    model = esme.ESM2(layers, D, H)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    lens = synthetic.synthetic_lengths(600000, seed=7)
+    tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=8)
+    assert tokens.numel() * 3 * D > 2 ** 31
+    out = model(tokens.to(DEV), (cu.to(DEV), max_len))
+    assert torch.isfinite(out.float()).all()
+    for s in (0, len(lens) // 2, len(lens) - 1):
+        a, b = int(cu[s]), int(cu[s + 1])
+        alone = model(tokens[a:b].contiguous().to(DEV), (torch.tensor([0, b - a], dtype=torch.int32, device=DEV), b - a))
+        assert torch.equal(out[a:b], alone), s
+    del out
+    torch.cuda.empty_cache()
