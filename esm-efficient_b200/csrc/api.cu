@@ -105,6 +105,11 @@ int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_max, int V
                           void* gathered, void* out, esmk_stream_t s) {
   GUARD(esmk::allgather_logits(comm, local, t_max, V, perm, T, gathered, out, ST(s)));
 }
+int esmk_comm_enable_peer(esmk_comm_t* comm, size_t buffer_bytes) { GUARD(esmk::comm_enable_peer(comm, buffer_bytes)); }
+int esmk_peer_allgather_logits(esmk_comm_t* comm, const void* local, int rows, int V, const int32_t* dest_rows, int T,
+                               void* out, esmk_stream_t s) {
+  GUARD(esmk::peer_allgather_logits(comm, local, rows, V, dest_rows, T, out, ST(s)));
+}
 void esmk_profile_enable(int on) { esmk::profile_enable(on); }
 int esmk_profile_read(float* ms, int* launches, int n_categories) {
   if (ms == nullptr || launches == nullptr) return esmk::fail("esmk_profile_read", "null argument");

@@ -55,9 +55,10 @@ int consume_async_error() {
   const uint32_t code = *reinterpret_cast<volatile uint32_t*>(word);
   if (code == 0) return 0;
   *reinterpret_cast<volatile uint32_t*>(word) = 0;
-  std::string msg = "a previous kernel reported invalid input data:";
+  std::string msg = "a previous kernel reported:";
   if (code & ESMK_ASYNC_BAD_TOKEN) msg += " token id outside [0, embedding rows) in esmk_embed / esmk_forward;";
   if (code & ESMK_ASYNC_BAD_POSITION) msg += " sequence longer than the learned positional table in esmk_add_positions;";
+  if (code & ESMK_ASYNC_PEER_TIMEOUT) msg += " a rank did not arrive within 30 s in esmk_peer_allgather_logits;";
   msg += " the outputs of that call are invalid";
   return fail("esmk (asynchronous)", msg);
 }

@@ -17,8 +17,9 @@ import torch.distributed as dist
 
 
 class EsmkComm:
-    """NCCL communicator owned by libesmk (esmk_comm_t): the collective of the path runs behind the C ABI
-    (esmk_allgather_logits = ncclAllGather + packed-order row gather).  torch.distributed is only used to hand the
+    """Communicator owned by libesmk (esmk_comm_t): the collective of the path runs behind the C ABI, either as direct
+    NVLink peer stores into every rank's window (esmk_peer_allgather_logits, after enable_peer) or as
+    esmk_allgather_logits = ncclAllGather + packed-order row gather.  torch.distributed is only used to hand the
     128-byte NCCL unique id from rank 0 to the other ranks."""
 
     def __init__(self, group=None, device=None):
@@ -45,6 +46,29 @@ class EsmkComm:
             os.dup2(saved, 1)
             os.close(saved)
 
+    peer_bytes = 0          # size of one buffer of the peer window (0: not enabled)
+
+    def enable_peer(self, buffer_bytes: int) -> bool:
+        """Collective: map every rank's window (CUDA IPC).  False where that is impossible -- on every rank alike."""
+        L = self.L
+        with torch.cuda.device(self.device):
+            rc = L.lib.esmk_comm_enable_peer(self.handle, int(buffer_bytes))
+        if rc != 0:
+            self.peer_error = L.lib.esmk_last_error().decode()
+            return False
+        self.peer_bytes = int(buffer_bytes)
+        return True
+
+    def peer_allgather_rows(self, local: torch.Tensor, dest_rows: torch.Tensor, out: torch.Tensor):
+        """local [T_r, V] bf16 (this rank's rows), dest_rows int32 [T_r] (their packed rows) -> out [T, V]."""
+        L = self.L
+        rows, V = local.shape
+        with torch.cuda.device(self.device):
+            L.check(L.lib.esmk_peer_allgather_logits(self.handle, local.data_ptr() if rows else None, rows, V,
+                                                     dest_rows.data_ptr() if rows else None, out.shape[0], out.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream), 'esmk_peer_allgather_logits')
+        return out
+
     def allgather_rows(self, local: torch.Tensor, perm: torch.Tensor, gathered: torch.Tensor, out: torch.Tensor):
         L = self.L
         t_max, V = local.shape
@@ -60,6 +84,17 @@ class EsmkComm:
                 self.L.lib.esmk_comm_destroy(self.handle)
         except Exception:
             pass
+
+
+_COMMS = {}
+
+
+def get_comm(group, device) -> EsmkComm:
+    """One libesmk communicator per (process group, device), created on first use (collective over the group)."""
+    key = (id(group) if group is not None else 0, torch.device(device).index)
+    if key not in _COMMS:
+        _COMMS[key] = EsmkComm(group, device)
+    return _COMMS[key]
 
 
 def sequence_cost(length: int, embed_dim: int, ffn_factor: float = 24.0) -> float:
@@ -122,33 +157,52 @@ class ShardPlan:
         for r, s in enumerate(self.shares):
             perm[s[3]] = torch.arange(s[3].numel(), dtype=torch.int64) + r * self.t_max
         self.perm = perm.to(device)
+        self.dest_rows = self.token_index.to(torch.int32).to(device)      # packed row of each of this rank's rows
         self._local = self._gathered = None
         self.comm: Optional[EsmkComm] = None      # created on the first CUDA gather (collective over the group)
         self.collective = None                    # which implementation ran the collective (reported by bench.py)
 
+    PEER = 'esmk_peer_allgather_logits (direct NVLink peer stores into every rank\'s window + flag handshake in libesmk, C ABI; no NCCL on the data path)'
+    NCCL = 'esmk_allgather_logits (ncclAllGather + row gather in libesmk, C ABI)'
+
     def gather(self, out: torch.Tensor, group=None) -> torch.Tensor:
-        """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank."""
+        """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank.
+        ESMK_COLLECTIVE = peer (default where CUDA IPC works) | nccl | torch selects the implementation."""
         width = out.shape[1]
-        if self._local is None or self._local.shape[1] != width or self._local.dtype != out.dtype:
-            self._local = torch.zeros(self.t_max, width, dtype=out.dtype, device=self.device)
-            self._gathered = torch.empty(self.world * self.t_max, width, dtype=out.dtype, device=self.device)
-        self._local[:out.shape[0]] = out
-        if out.is_cuda and out.dtype == torch.bfloat16 and os.environ.get('ESMK_COLLECTIVE', 'esmk') != 'torch':
-            # the only collective of the path, behind the C ABI: ncclAllGather + packed-order row gather in libesmk
+        want = os.environ.get('ESMK_COLLECTIVE', 'peer')
+        if out.is_cuda and out.dtype == torch.bfloat16 and want != 'torch':
             if self.comm is None and self.collective is None:
                 try:
-                    self.comm = EsmkComm(group, self.device)
-                    self.collective = 'esmk_allgather_logits (ncclAllGather + row gather in libesmk, C ABI)'
+                    self.comm = get_comm(group, self.device)
                 except Exception as e:      # e.g. no loadable libnccl.so.2: every rank fails alike (same image)
                     print(f'esme.parallel: libesmk communicator unavailable ({e}); using torch.distributed NCCL', file=sys.stderr)
                     self.collective = 'torch.distributed.all_gather_into_tensor (NCCL) + index_select'
             if self.comm is not None:
                 result = torch.empty(self.T, width, dtype=out.dtype, device=self.device)
+                need = self.T * width * out.element_size()
+                if want == 'peer' and self.comm.peer_bytes == 0 and not getattr(self.comm, 'peer_failed', False):
+                    # window sized for batches up to 4x this one (every rank sees the same T: same decision everywhere)
+                    if not self.comm.enable_peer(max(4 * need, 64 << 20)):
+                        self.comm.peer_failed = True
+                        print(f'esme.parallel: NVLink peer window unavailable ({self.comm.peer_error}); using ncclAllGather',
+                              file=sys.stderr)
+                if want == 'peer' and self.comm.peer_bytes >= need:
+                    self.collective = self.PEER
+                    return self.comm.peer_allgather_rows(out.contiguous(), self.dest_rows, result)
+                self.collective = self.NCCL
+                self._stage(out, width)
                 return self.comm.allgather_rows(self._local, self.perm, self._gathered, result)
         if self.collective is None:
             self.collective = 'torch.distributed.all_gather_into_tensor + index_select'
+        self._stage(out, width)
         dist.all_gather_into_tensor(self._gathered, self._local, group=group)      # (CPU / gloo tests, ESMK_COLLECTIVE=torch)
         return self._gathered.index_select(0, self.perm)
+
+    def _stage(self, out: torch.Tensor, width: int):
+        if self._local is None or self._local.shape[1] != width or self._local.dtype != out.dtype:
+            self._local = torch.zeros(self.t_max, width, dtype=out.dtype, device=self.device)
+            self._gathered = torch.empty(self.world * self.t_max, width, dtype=out.dtype, device=self.device)
+        self._local[:out.shape[0]] = out
 
 
 def sharded_forward(fn: Callable[[torch.Tensor, torch.Tensor, int], torch.Tensor], tokens: torch.Tensor,

@@ -41,8 +41,9 @@ ESMK_API int esmk_version(void);
  * the embedding table -- the reference would trip a device-side assert in F.embedding, esme/esm.py:187 -- or a
  * sequence longer than the learned positional table, esme/embedding.py) sets a sticky flag that makes the NEXT entry
  * point called after the kernel ran fail with a message naming the cause (the flag is then cleared).
- * esmk_async_error() polls and clears it explicitly: 0 or a bit-or of the codes below. */
-enum esmk_async_code { ESMK_ASYNC_BAD_TOKEN = 1, ESMK_ASYNC_BAD_POSITION = 2 };
+ * esmk_async_error() polls and clears it explicitly: 0 or a bit-or of the codes below (ESMK_ASYNC_PEER_TIMEOUT: a rank
+ * never arrived in esmk_peer_allgather_logits). */
+enum esmk_async_code { ESMK_ASYNC_BAD_TOKEN = 1, ESMK_ASYNC_BAD_POSITION = 2, ESMK_ASYNC_PEER_TIMEOUT = 4 };
 ESMK_API int esmk_async_error(void);
 /* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
 ESMK_API uint64_t esmk_launch_count(void);
@@ -270,6 +271,19 @@ ESMK_API int esmk_comm_create(esmk_comm_t** out, int world_size, int rank, const
 ESMK_API void esmk_comm_destroy(esmk_comm_t* comm);
 ESMK_API int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_max, int V, const int64_t* perm, int T,
                                    void* gathered, void* out, esmk_stream_t stream);
+/* The same collective over NVLink / NVSwitch peer memory, without NCCL on the data path ("direct peer
+ * stores ... into a symmetric buffer").
+ *   esmk_comm_enable_peer     : collective over all ranks (one node); allocates this rank's window -- two buffers of
+ *       buffer_bytes >= T*V*2 each -- exchanges CUDA IPC handles and maps every peer's window.  Non-zero where CUDA IPC
+ *       or peer access is unavailable (same outcome on every rank): keep using esmk_allgather_logits then.
+ *   esmk_peer_allgather_logits: local [rows, V] bf16 = this rank's rows, dest_rows int32[rows] (device) = packed row of
+ *       each -> out [T, V] holding all ranks' rows in packed order.  One kernel stores the rows at their final position
+ *       in EVERY rank's window and publishes a per-rank flag (system-scope release); a one-block kernel waits for all
+ *       ranks' flags; the window is then copied to out.  All calls of one communicator must be issued on ONE stream, in
+ *       the same order on every rank; a peer that never arrives sets ESMK_ASYNC_PEER_TIMEOUT after 30 s. */
+ESMK_API int esmk_comm_enable_peer(esmk_comm_t* comm, size_t buffer_bytes);
+ESMK_API int esmk_peer_allgather_logits(esmk_comm_t* comm, const void* local, int rows, int V, const int32_t* dest_rows,
+                                        int T, void* out, esmk_stream_t stream);
 
 /* ---- per-kernel-family device timing (measurement only) ------------------------- */
 enum esmk_prof_category {
