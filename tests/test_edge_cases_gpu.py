@@ -167,3 +167,27 @@ def test_batch_with_more_than_2_31_activation_elements():
         assert torch.equal(out[a:b], alone), s
     del out
     torch.cuda.empty_cache()
+
+
+def test_repeated_forwards_are_bit_identical_under_interference():
+    """30 forwards of a 650M-width model (TMA-store and TMA-residual epilogues, two CTAs per SM in attention) while a
+    second stream keeps HBM and L2 busy: every result equals the first bit for bit (a staging-slot or barrier race
+    would show as run-to-run differences)."""
+    layers, D, H = 2, 1280, 20
+    sd = synthetic.synthetic_state_dict('esm2', layers, D, seed=3)
+    model = esme.ESM2(layers, D, H)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    lens = synthetic.synthetic_lengths(20000, seed=12)
+    tokens, cu, max_len = synthetic.synthetic_batch(lens, seed=13)
+    tokens, cu = tokens.to(DEV), cu.to(DEV)
+    first = model(tokens, (cu, max_len)).clone()
+    noise = torch.empty(64 << 20, dtype=torch.float32, device=DEV)
+    side = torch.cuda.Stream()
+    for i in range(30):
+        if i % 2:
+            with torch.cuda.stream(side):
+                noise.normal_()
+                noise.mul_(1.0001)
+        assert torch.equal(model(tokens, (cu, max_len)), first), i
+    torch.cuda.synchronize()
