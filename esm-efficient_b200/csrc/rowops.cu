@@ -341,12 +341,15 @@ template <int NCH>
 __global__ void __launch_bounds__(kRowWarps * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, int ldy, int T, int D,
-                 float eps) {
+                 float eps, int reverse) {
   griddep_launch_dependents();
   griddep_wait();
   int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= T) return;
+  // Rows are walked from the LAST to the first: x was just written front to back by the residual GEMM, so its tail is
+  // what the L2 still holds, and the rows written last here (the first ones) are the ones the next GEMM reads first.
+  if (reverse) row = T - 1 - row;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * ldx);
   const int D8 = D >> 3;
   uint64_t v[NCH][4];
@@ -404,9 +407,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat
 template <int NCH>
 static void launch_ln(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
                       cudaStream_t st) {
+  static const int reverse = [] { const char* e = getenv("ESMK_LN_REVERSE"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
   launch_pdl(layernorm_kernel<NCH>, dim3((T + kRowWarps - 1) / kRowWarps), dim3(kRowWarps * 32), 0, st,
       (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, ldy, T, D,
-      eps);
+      eps, reverse);
 }
 
 int layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int T, int D, float eps,
