@@ -167,9 +167,9 @@ class ShardPlan:
 
     def gather(self, out: torch.Tensor, group=None) -> torch.Tensor:
         """out: this rank's [T_r, width] result -> [T, width] in the original packed order, on every rank.
-        ESMK_COLLECTIVE = peer (default where CUDA IPC works) | nccl | torch selects the implementation."""
+        ESMK_COLLECTIVE = nccl (default) | peer (NVLink peer stores, opt-in) | torch selects the implementation."""
         width = out.shape[1]
-        want = os.environ.get('ESMK_COLLECTIVE', 'peer')
+        want = os.environ.get('ESMK_COLLECTIVE', 'nccl')
         if out.is_cuda and out.dtype == torch.bfloat16 and want != 'torch':
             if self.comm is None and self.collective is None:
                 try:
