@@ -513,6 +513,7 @@ def main():
             sharded_ok = bool(torch.equal(single, full_logits[:c[n]]))
     if rank != 0:
         if world > 1:
+            parallel.close_comms()      # libesmk communicator released in step on all ranks, before any rank exits
             dist.barrier()
             dist.destroy_process_group()
         return
@@ -608,6 +609,7 @@ def main():
         result['collective'] = plan.collective
     emit(result)
     if world > 1:
+        parallel.close_comms()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -106,6 +106,7 @@ int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_max, int V
   GUARD(esmk::allgather_logits(comm, local, t_max, V, perm, T, gathered, out, ST(s)));
 }
 int esmk_comm_enable_peer(esmk_comm_t* comm, size_t buffer_bytes) { GUARD(esmk::comm_enable_peer(comm, buffer_bytes)); }
+int esmk_comm_disable_peer(esmk_comm_t* comm) { GUARD(esmk::comm_disable_peer(comm)); }
 int esmk_peer_allgather_logits(esmk_comm_t* comm, const void* local, int rows, int V, const int32_t* dest_rows, int T,
                                void* out, esmk_stream_t s) {
   GUARD(esmk::peer_allgather_logits(comm, local, rows, V, dest_rows, T, out, ST(s)));

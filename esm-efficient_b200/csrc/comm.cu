@@ -192,13 +192,41 @@ int comm_create(esmk_comm** out, int world, int rank, const void* id128) {
   return 0;
 }
 
+// Collective: every rank unmaps its peers' windows, all ranks meet (one-byte ncclAllGather), and only then does each
+// rank free its own window -- CUDA leaves a cudaFree of exported memory that another process still has mapped undefined.
+int comm_disable_peer(esmk_comm* c) {
+  ESMK_REQUIRE(c != nullptr, "null communicator");
+  if (c->window == nullptr) return 0;
+  ESMK_REQUIRE(c->device == current_device(), "the communicator belongs to another device");
+  ESMK_CUDA(cudaDeviceSynchronize());
+  for (int p = 0; p < (int)c->mapped.size(); ++p)
+    if (p != c->rank && c->mapped[p] != nullptr) cudaIpcCloseMemHandle(c->mapped[p]);
+  c->mapped.clear();
+  uint8_t* vote = nullptr;
+  ESMK_CUDA(cudaMalloc(&vote, (size_t)c->world + 1));
+  const int rc = nccl().all_gather(vote + c->world, vote, 1, 0, c->comm, nullptr);
+  if (rc == 0) cudaStreamSynchronize(nullptr);
+  cudaFree(vote);
+  if (rc != 0) return nccl_fail("ncclAllGather (peer tear-down barrier)", rc);   // (the window stays allocated)
+  cudaFree(c->windows_dev);
+  cudaFree(c->counter);
+  cudaFree(c->window);
+  c->windows_dev = nullptr;
+  c->counter = nullptr;
+  c->window = nullptr;
+  c->half_bytes = 0;
+  return 0;
+}
+
 void comm_destroy(esmk_comm* c) {
   if (c == nullptr) return;
+  // Not a collective: if the peer windows are still up (esmk_comm_disable_peer was not called) the imports are
+  // closed, but this rank's own window is deliberately NOT freed -- a peer may still have it mapped -- and goes
+  // with the process.
   for (int p = 0; p < (int)c->mapped.size(); ++p)
     if (p != c->rank && c->mapped[p] != nullptr) cudaIpcCloseMemHandle(c->mapped[p]);
   if (c->windows_dev != nullptr) cudaFree(c->windows_dev);
   if (c->counter != nullptr) cudaFree(c->counter);
-  if (c->window != nullptr) cudaFree(c->window);
   if (c->comm != nullptr && nccl().ok) nccl().comm_destroy(c->comm);
   delete c;
 }

@@ -51,6 +51,7 @@ void comm_destroy(esmk_comm* c);
 int allgather_logits(esmk_comm* c, const void* local, int t_max, int V, const int64_t* perm, int T, void* gathered,
                      void* out, cudaStream_t st);
 int comm_enable_peer(esmk_comm* c, size_t buffer_bytes);
+int comm_disable_peer(esmk_comm* c);
 int peer_allgather_logits(esmk_comm* c, const void* local, int rows, int V, const int32_t* dest_rows, int T, void* out,
                           cudaStream_t st);
 

@@ -108,6 +108,7 @@ SIGNATURES = {
     'esmk_comm_destroy': (None, [c_void_p]),
     'esmk_allgather_logits': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'esmk_comm_enable_peer': (c_int, [c_void_p, c_size_t]),
+    'esmk_comm_disable_peer': (c_int, [c_void_p]),
     'esmk_peer_allgather_logits': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'esmk_profile_enable': (None, [c_int]),
     'esmk_profile_read': (c_int, [C.POINTER(c_float), C.POINTER(c_int), c_int]),

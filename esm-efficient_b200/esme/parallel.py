@@ -78,15 +78,39 @@ class EsmkComm:
                                                 torch.cuda.current_stream().cuda_stream), 'esmk_allgather_logits')
         return out
 
+    def close(self, collective: bool = False):
+        """Release the communicator (NCCL comm, peer windows and mappings).  Call it on every rank while all ranks are
+        still alive -- close_comms() does, behind a barrier -- rather than leaving it to interpreter shutdown."""
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                if collective and self.peer_bytes:
+                    self.L.lib.esmk_comm_disable_peer(handle)      # unmap peers, meet, free the window (in that order)
+                self.L.lib.esmk_comm_destroy(handle)
+        self.peer_bytes = 0
+
     def __del__(self):
         try:
-            if getattr(self, 'handle', None):
-                self.L.lib.esmk_comm_destroy(self.handle)
+            self.close()
         except Exception:
             pass
 
 
 _COMMS = {}
+
+
+def close_comms(group=None):
+    """Collective: destroy the cached libesmk communicators in step on all ranks (device idle, nobody mid-collective)."""
+    if not _COMMS:
+        return
+    if dist.is_initialized():
+        dist.barrier(group)
+    for comm in list(_COMMS.values()):
+        comm.close(collective=True)
+    _COMMS.clear()
+    if dist.is_initialized():
+        dist.barrier(group)
 
 
 def get_comm(group, device) -> EsmkComm:

@@ -280,8 +280,12 @@ ESMK_API int esmk_allgather_logits(esmk_comm_t* comm, const void* local, int t_m
  *       each -> out [T, V] holding all ranks' rows in packed order.  One kernel stores the rows at their final position
  *       in EVERY rank's window and publishes a per-rank flag (system-scope release); a one-block kernel waits for all
  *       ranks' flags; the window is then copied to out.  All calls of one communicator must be issued on ONE stream, in
- *       the same order on every rank; a peer that never arrives sets ESMK_ASYNC_PEER_TIMEOUT after 30 s. */
+ *       the same order on every rank; a peer that never arrives sets ESMK_ASYNC_PEER_TIMEOUT after 30 s.
+ *   esmk_comm_disable_peer    : collective; unmaps the peers' windows, meets all ranks, then frees this rank's window
+ *       (CUDA leaves freeing exported memory that a peer still maps undefined).  Call it before esmk_comm_destroy;
+ *       a communicator destroyed with its windows up leaves its own window to process exit. */
 ESMK_API int esmk_comm_enable_peer(esmk_comm_t* comm, size_t buffer_bytes);
+ESMK_API int esmk_comm_disable_peer(esmk_comm_t* comm);
 ESMK_API int esmk_peer_allgather_logits(esmk_comm_t* comm, const void* local, int rows, int V, const int32_t* dest_rows,
                                         int T, void* out, esmk_stream_t stream);
 

@@ -41,6 +41,7 @@ def _worker(rank, world, port, ret, collective):
             used = plan.collective
         want_impl = {'peer': 'esmk_peer_allgather_logits', 'nccl': 'esmk_allgather_logits', 'torch': 'torch.distributed'}
         ret[rank] = ok and used.startswith(want_impl[collective])
+        parallel.close_comms()
     finally:
         dist.destroy_process_group()
 
