@@ -441,13 +441,15 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int ld, int T, int D, int hd,
                     const __nv_bfloat16* __restrict__ lnq, const __nv_bfloat16* __restrict__ lnk,
                     const __nv_bfloat16* __restrict__ cosb, const __nv_bfloat16* __restrict__ sinb,
-                    const int32_t* __restrict__ pos) {
+                    const int32_t* __restrict__ pos, int reverse) {
   // adjacent warps take the q and the k part of the same token: with q | k | v in one row the two parts are
   // contiguous in memory, which keeps the DRAM pages of the row open for both
   const int item = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
-  const int row = item >> 1, which = item & 1;
+  int row = item >> 1;
+  const int which = item & 1;
   int lane = threadIdx.x & 31;
   if (row >= T) return;
+  if (reverse) row = T - 1 - row;      // last rows first: the tail of the QKV GEMM's output is what the L2 still holds
   __nv_bfloat16* base = (which == 0 ? q : k) + (size_t)row * ld;
   const __nv_bfloat16* lnw = which == 0 ? lnq : lnk;
   uint4* xr = reinterpret_cast<uint4*>(base);
@@ -573,9 +575,10 @@ template <int NCH>
 static void launch_qk(void* q, void* k, int ld, int T, int D, int hd, const void* lnq, const void* lnk,
                       const void* cosb, const void* sinb, const int32_t* pos, cudaStream_t st) {
   dim3 grid((2 * T + kRowWarps - 1) / kRowWarps);
+  static const int reverse = [] { const char* e = getenv("ESMK_LN_REVERSE"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
   qk_norm_rope_kernel<NCH><<<grid, kRowWarps * 32, 0, st>>>(
       (__nv_bfloat16*)q, (__nv_bfloat16*)k, ld, T, D, hd, (const __nv_bfloat16*)lnq, (const __nv_bfloat16*)lnk,
-      (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, pos);
+      (const __nv_bfloat16*)cosb, (const __nv_bfloat16*)sinb, pos, reverse);
 }
 
 int qk_norm_rope(void* q, void* k, int ld, int T, int H, int hd, const void* lnq, const void* lnk, const void* cosb,
