@@ -47,6 +47,7 @@ constexpr int BAR_REGION = 1024;
 // thread (32 half-used sectors per instruction; ncu: long_scoreboard 11-40 warps per issue in the epilogue of the
 // N = 1280 GEMMs).  The result is written back into the same slot and leaves through one TMA store.  That needs
 // 4 KB per epilogue warp (64 KB), paid for with one pipeline stage (5 instead of 6).
+constexpr int kStaggerNsPerK = 40;     // RESIDUAL epilogue: start-time spread of the column groups (launch code below)
 constexpr int STAGES_PAIR_RESID = 5;
 constexpr int STORE_STAGING_RESID = 64 * 1024;
 static_assert(STAGES_PAIR_RESID * (BM * BK * 2 + BN * BK) + STORE_STAGING_RESID == 6 * (BM * BK * 2 + BN * BK) + STORE_STAGING,
@@ -70,6 +71,7 @@ struct EpiParams {
   int vec_ok;  // 16-byte accesses allowed on C / R / bias (alignment and N % 8 == 0)
   int tma_store;  // tmC is valid: whole 64-column groups leave through shared memory + TMA stores
   int tma_resid;  // RESIDUAL, pair mode: tmR is valid and tmC has 32 x 64 boxes (residual prefetched by TMA)
+  int stagger_ns; // 16-warp epilogues: column group cg starts cg * stagger_ns after the accumulator is complete
 };
 
 // exact-erf GELU:  gelu(x) = relu(x) - |x| * erfc(|x| / sqrt 2) / 2,
@@ -388,6 +390,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t bias_w = 0;                         // columns n0 + 2*lane, n0 + 2*lane + 1; handed out by shuffles
           if (has_bias) bias_w = __ldg(reinterpret_cast<const uint32_t*>(ep.bias + n0) + lane);
           mbar_wait(&acc_full[as], aphase);
+          // The 16 epilogue warps of all CTAs would otherwise fire together at every tile boundary -- a burst of
+          // residual reads and output stores exactly when the producers open the next tiles' cold A rows.  The four
+          // column groups start stagger_ns apart instead (not on a pair's last tile: nothing follows it).
+          if (ep.stagger_ns > 0 && cg > 0 && tile + n_groups < num_tiles) __nanosleep(cg * ep.stagger_ns);
           tc_fence_after();
           mbar_wait(rbar, r_phase);
           r_phase ^= 1;
@@ -465,6 +471,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 
       mbar_wait(&acc_full[as], aphase);
+      if (ep.stagger_ns > 0 && cg > 0 && tile + n_groups < num_tiles) __nanosleep(cg * ep.stagger_ns);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + cg * 64;
 
@@ -928,6 +935,10 @@ int gemm(const esmk_gemm_args& a, cudaStream_t st) {
   CUtensorMap tmR = tmA;
   ep.tma_store = 0;
   ep.tma_resid = 0;
+  // RESIDUAL epilogue: the four 64-column groups of a tile start stagger_ns apart (ns per k-block of the main loop, so
+  // the spread scales with the time the next tile's MMAs give the epilogue)
+  static const int stagger_per_k = [] { const char* e = getenv("ESMK_GEMM_EPI_STAGGER_NS_PER_K"); return e ? atoi(e) : kStaggerNsPerK; }();
+  ep.stagger_ns = a.epilogue == ESMK_EPI_RESIDUAL ? stagger_per_k * ((a.K + BK - 1) / BK) : 0;
   static const bool tma_resid_enabled = [] { const char* e = getenv("ESMK_GEMM_TMA_RESID"); return e == nullptr || e[0] != '0'; }();
   if (ep.vec_ok && tma_store_enabled) {
     if (pair && a.epilogue == ESMK_EPI_RESIDUAL && tma_resid_enabled && a.R != nullptr) {
