@@ -20,6 +20,27 @@ def test_partition_is_a_balanced_cover():
     assert P.partition_sequences([5], 4) == [[0], [], [], []]
 
 
+def test_shard_plan_row_maps_agree():
+    """The two row maps of a ShardPlan describe the same permutation: perm (packed row -> row of the rank-major padded
+    all-gather buffer, used by esmk_allgather_logits) and dest_rows (this rank's row -> packed row, used by the peer
+    path's direct stores); every packed row is owned by exactly one rank."""
+    lens = [40, 7, 300, 2, 128, 129, 64, 5]
+    tokens, cu, _ = O.synthetic_batch(lens, seed=9)
+    for world in (1, 2, 3, 8, 16):                    # 16 ranks: some own nothing
+        plans = [P.ShardPlan(tokens, cu, world, r, 64, 'cpu') for r in range(world)]
+        T = int(cu[-1])
+        seen = torch.zeros(T, dtype=torch.int64)
+        for r, pl in enumerate(plans):
+            assert pl.dest_rows.dtype == torch.int32 and pl.dest_rows.numel() == pl.tokens.numel()
+            seen[pl.dest_rows.long()] += 1
+            assert torch.equal(tokens[pl.dest_rows.long()], pl.tokens)
+            # row i of rank r sits at r * t_max + i in the gathered buffer
+            assert torch.equal(pl.perm[pl.dest_rows.long()], torch.arange(pl.tokens.numel()) + r * pl.t_max)
+            assert torch.equal(pl.perm, plans[0].perm) and pl.t_max == plans[0].t_max
+        assert bool((seen == 1).all())
+    P.close_comms()                                   # nothing cached on the CPU path: a no-op
+
+
 def _fake_forward(tokens, cu_lens, max_len):
     """Deterministic stand-in for the per-rank GPU forward: depends on the token, its position
     inside its own sequence and that sequence's length (so wrong sharding / ordering shows)."""
